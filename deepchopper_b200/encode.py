@@ -1,0 +1,185 @@
+"""FASTQ ingest + GPU encoder: host mirror of parse_fastq_file (deepchopper/data/only_fq.py:21-85),
+encode_qual / normalize_seq (src/python.rs:25-35,272-275), tokenize_and_align_labels_and_quals_ids
+(deepchopper/models/llm/tokenizer.py:145-178) and the LEFT-padding collator (tokenizer.py:34-93).
+
+The host only finds record boundaries (newline index); the bytes -> token / normalised-quality
+work runs in dcb200_encode_batch on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from ._native import check, lib
+
+MAX_TOKENS = 32768          # tokenizer max_length passed by the reference (tokenizer.py:96-114)
+MAX_ID_LENGTH = 256         # tokenizer.py:146
+PAD, SEP = 4, 1
+
+
+def encode_qual(qual: str, qual_offset: int = 33) -> List[int]:
+    """deepchopper.encode_qual (src/python.rs:25-35)."""
+    a = np.frombuffer(qual.encode("latin1"), dtype=np.uint8).astype(np.int64) - int(qual_offset)
+    if a.size and a.min() < 0:
+        raise OverflowError("quality character below the offset")   # Rust u8 subtraction panics
+    return a.tolist()
+
+
+_NORM = np.full(256, ord("N"), dtype=np.uint8)
+for _c in b"ACGTN-":
+    _NORM[_c] = _c
+for _a, _b in zip(b"acgtn", b"ACGTN"):
+    _NORM[_a] = _b
+_NORM[ord("U")] = _NORM[ord("u")] = ord("T")
+_NORM[ord(".")] = _NORM[ord("~")] = ord("-")
+
+
+def normalize_seq(seq: str, iupac: bool = False) -> str:
+    """deepchopper.normalize_seq (src/python.rs:272-275, needletail normalize, iupac=False)."""
+    if iupac:
+        raise NotImplementedError("iupac=True is not on the predict path")
+    a = np.frombuffer(seq.encode("latin1"), dtype=np.uint8)
+    a = a[(a != 32) & (a != 9) & (a != 13) & (a != 10)]
+    return _NORM[a].tobytes().decode("ascii")
+
+
+@dataclass
+class FastqIndex:
+    """Record boundaries inside one FASTQ byte buffer (4-line records)."""
+    buf: np.ndarray            # uint8, the whole text
+    name_off: np.ndarray       # int64 [R] offset of the byte after '@'
+    name_len: np.ndarray       # int32 [R] length of the id (up to the first blank)
+    head_len: np.ndarray       # int32 [R] length of the full header line after '@'
+    seq_off: np.ndarray        # int64 [R]
+    seq_len: np.ndarray        # int32 [R]
+    qual_off: np.ndarray       # int64 [R]
+    qual_len: np.ndarray       # int32 [R]
+
+    def __len__(self):
+        return int(self.seq_off.size)
+
+    def name(self, r: int) -> str:
+        o = int(self.name_off[r])
+        return self.buf[o:o + int(self.name_len[r])].tobytes().decode("ascii", "replace")
+
+    def header(self, r: int) -> str:
+        o = int(self.name_off[r])
+        return self.buf[o:o + int(self.head_len[r])].tobytes().decode("ascii", "replace")
+
+    def seq(self, r: int) -> bytes:
+        o = int(self.seq_off[r])
+        return self.buf[o:o + int(self.seq_len[r])].tobytes()
+
+    def qual(self, r: int) -> bytes:
+        o = int(self.qual_off[r])
+        return self.buf[o:o + int(self.qual_len[r])].tobytes()
+
+
+def read_fastq_bytes(path: str) -> np.ndarray:
+    """Plain / gzip / bgzip FASTQ -> uint8 array (compression sniffed like src/output/writefq.rs:84-135)."""
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        with gzip.open(path, "rb") as f:
+            data = f.read()
+    else:
+        with open(path, "rb") as f:
+            data = f.read()
+    return np.frombuffer(data, dtype=np.uint8)
+
+
+def index_fastq(buf: np.ndarray) -> FastqIndex:
+    """Vectorised newline index.  Validates like only_fq.py:38-85: '@' headers, equal seq/qual lengths."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    nl = np.flatnonzero(buf == 10)
+    if buf.size and (nl.size == 0 or nl[-1] != buf.size - 1):
+        nl = np.append(nl, buf.size)          # last line without trailing newline
+    line_start = np.concatenate([[0], nl[:-1] + 1]).astype(np.int64)
+    line_end = nl.astype(np.int64)
+    # strip '\r'
+    cr = (line_end > line_start) & (buf[np.maximum(line_end - 1, 0)] == 13)
+    line_end = line_end - cr
+    # drop trailing empty lines
+    nlines = line_start.size
+    while nlines and line_end[nlines - 1] == line_start[nlines - 1]:
+        nlines -= 1
+    if nlines % 4 != 0:
+        raise ValueError(f"FASTQ has {nlines} lines, not a multiple of 4")
+    R = nlines // 4
+    hs, he = line_start[0:nlines:4], line_end[0:nlines:4]
+    ss, se = line_start[1:nlines:4], line_end[1:nlines:4]
+    ps = line_start[2:nlines:4]
+    qs, qe = line_start[3:nlines:4], line_end[3:nlines:4]
+    if R:
+        if not (buf[hs] == ord("@")).all():
+            raise ValueError("FASTQ record does not start with '@'")
+        if not (buf[ps] == ord("+")).all():
+            raise ValueError("FASTQ separator line does not start with '+'")
+        if not ((se - ss) == (qe - qs)).all():
+            bad = int(np.flatnonzero((se - ss) != (qe - qs))[0])
+            raise ValueError(f"record {bad}: sequence and quality lengths differ")     # only_fq.py:49-57
+        if ((se - ss) == 0).any():
+            raise ValueError("empty sequence in FASTQ")                                # only_fq.py:44-47
+    head_len = (he - hs - 1).astype(np.int32)
+    # id = header up to the first blank
+    name_len = head_len.copy()
+    is_blank = (buf == 32) | (buf == 9)
+    blank_pos = np.flatnonzero(is_blank)
+    if blank_pos.size and R:
+        j = np.searchsorted(blank_pos, hs + 1)
+        has = j < blank_pos.size
+        first = np.where(has, blank_pos[np.minimum(j, blank_pos.size - 1)], np.iinfo(np.int64).max)
+        inside = first < he
+        name_len = np.where(inside, first - hs - 1, head_len).astype(np.int32)
+    return FastqIndex(buf, hs + 1, name_len, head_len, ss, (se - ss).astype(np.int32), qs, (qe - qs).astype(np.int32))
+
+
+def id_rows(index: FastqIndex, rows: Sequence[int], truncated: np.ndarray) -> np.ndarray:
+    """``id`` feature rows [len, truncated, ascii..., 0 pad] x 256 (tokenizer.py:169-175)."""
+    out = np.zeros((len(rows), MAX_ID_LENGTH), dtype=np.int64)
+    for k, r in enumerate(rows):
+        n = int(index.name_len[r])
+        o = int(index.name_off[r])
+        row = np.concatenate([[n, int(truncated[k])], index.buf[o:o + n].astype(np.int64)])[:MAX_ID_LENGTH]
+        out[k, : row.size] = row
+    return out
+
+
+def encode_batch_device(bytes_dev, seq_off_dev, qual_off_dev, len_dev, Lpad: int, ctx=None):
+    """dcb200_encode_batch on torch CUDA tensors -> (tok uint8 [R,Lpad], qual float32 [R,Lpad])."""
+    import torch
+    ctx = ctx or _native.torch_context(bytes_dev.device)
+    R = int(len_dev.numel())
+    tok = torch.empty((R, Lpad), dtype=torch.uint8, device=bytes_dev.device)
+    qual = torch.empty((R, Lpad), dtype=torch.float32, device=bytes_dev.device)
+    check(lib().dcb200_encode_batch(ctx.handle, C.c_void_p(bytes_dev.data_ptr()), C.c_void_p(seq_off_dev.data_ptr()),
+                                    C.c_void_p(qual_off_dev.data_ptr()), C.c_void_p(len_dev.data_ptr()), R, int(Lpad),
+                                    C.c_void_p(tok.data_ptr()), C.c_void_p(qual.data_ptr())))
+    return tok, qual
+
+
+def encode_records(recs: Sequence[Tuple[str, str, str]], Lpad: int, device="cuda"):
+    """Convenience: [(id, seq, qual)] -> device tensors through the GPU encoder."""
+    import torch
+    blob = bytearray()
+    so, qo, ln = [], [], []
+    for _, s, q in recs:
+        if len(s) != len(q):
+            raise ValueError("sequence and quality lengths differ")
+        n = min(len(s), MAX_TOKENS - 1)
+        so.append(len(blob))
+        blob += s.encode("latin1")
+        qo.append(len(blob))
+        blob += q.encode("latin1")
+        ln.append(n)
+    if max(ln) + 1 > Lpad:
+        raise ValueError("Lpad too small")
+    dev = torch.device(device)
+    b = torch.frombuffer(bytes(blob), dtype=torch.uint8).to(dev)
+    return encode_batch_device(b, torch.tensor(so, dtype=torch.int64, device=dev),
+                               torch.tensor(qo, dtype=torch.int64, device=dev),
+                               torch.tensor(ln, dtype=torch.int32, device=dev), Lpad)

@@ -1,0 +1,157 @@
+/* dcb200.h -- C ABI of the B200-native DeepChopper predict hot path.
+ *
+ * One shared library (libdcb200.so, sm_100a only) behind plain pointers and sizes: no torch, no
+ * C++ types.  Every entry point returns 0 on success or a negative DCB200_E* code;
+ * dcb200_last_error() returns a thread-local, human-readable message for the last failure.
+ * A dcb200_ctx owns one device + one stream (and its workspaces); it is not thread-safe, use
+ * one ctx per thread/GPU.  The caller owns every buffer passed in.
+ *
+ * "device" pointers must be device-accessible (cudaMalloc or pinned/UVA host memory);
+ * "host" pointers are ordinary host memory (the *_host entry points copy inside the call).
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   dcb200_encode_batch     deepchopper/data/only_fq.py:21-85 (parse_fastq_file), src/python.rs:25-35 (encode_qual),
+ *                           src/python.rs:272-275 (normalize_seq), deepchopper/models/llm/tokenizer.py:145-178
+ *                           (tokenize_and_align_labels_and_quals_ids) and :34-93 (collator, LEFT pad)
+ *   dcb200_weights_create   deepchopper/models/dc_hg.py:70-163 (from_checkpoint / from_pretrained state dict)
+ *   dcb200_forward          deepchopper/models/basic_module.py:90-100,197-207 -> deepchopper/models/llm/hyena.py:29-41
+ *                           (HyenaDNA backbone, HF remote code) -> deepchopper/models/llm/head.py:94-102
+ *   dcb200_majority_voting  src/smooth/utils.rs:48-97  (PyO3: src/python.rs:815-818)
+ *   dcb200_smooth_chop      src/smooth/predict.rs:186-209 (smooth_and_select_intervals) == src/utils.rs:699-721
+ *                           (smooth_label_region, PyO3 src/python.rs:674-690), src/utils.rs:671-695 (get_label_region),
+ *                           src/output/split.rs:60-136,171-226,260-320 and the gating of src/bin/predict.rs:137-187
+ *   dcb200_smooth_chop_logits  the same after src/smooth/predict.rs:263-317 (argmax(2) + drop target == -100)
+ *   dcb200_predict_batch_host  the whole per-batch hot loop of `deepchopper predict` + the interval step of
+ *                           `deepchopper chop` (cli.py:66-152, src/bin/predict.rs:130-192) on host buffers
+ */
+#ifndef DCB200_H_
+#define DCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB200_OK 0
+#define DCB200_EINVAL (-1)   /* bad argument */
+#define DCB200_ECUDA (-2)    /* CUDA runtime / driver error (message has the CUDA string) */
+#define DCB200_ENOMEM (-3)
+#define DCB200_ENODEV (-4)   /* no sm_100 device: this library has no CPU fallback */
+#define DCB200_EWEIGHT (-5)  /* missing / mis-shaped tensor in the state dict */
+
+/* per-read action of the chop step (src/bin/predict.rs:141-187) */
+#define DCB200_ACTION_PASSTHROUGH 0 /* emit the FASTQ record verbatim */
+#define DCB200_ACTION_CHOP_T 1      /* emit keep_iv pieces named "{id}|s:e|T" */
+#define DCB200_ACTION_CHOP_I 2      /* emit keep_iv pieces named "{id}|s:e|I" */
+#define DCB200_ACTION_ADAPTERS 3    /* --ocq: emit adapter_iv pieces named "{id}|s:e" */
+
+#define DCB200_CHOP_TERMINAL 0
+#define DCB200_CHOP_INTERNAL 1
+#define DCB200_CHOP_ALL 2
+
+/* token ids of the HyenaDNA character tokenizer (src/smooth/utils.rs:6-25) */
+#define DCB200_TOK_SEP 1
+#define DCB200_TOK_PAD 4
+#define DCB200_TOK_UNK 6
+#define DCB200_TOK_A 7
+#define DCB200_TOK_C 8
+#define DCB200_TOK_G 9
+#define DCB200_TOK_T 10
+#define DCB200_TOK_N 11
+
+typedef struct dcb200_ctx dcb200_ctx;
+typedef struct dcb200_weights dcb200_weights;
+
+/* clap defaults of deepchopper-chop (src/bin/predict.rs:19-78) + src/default.rs */
+typedef struct dcb200_chop_params {
+  int32_t smooth_window_size;         /* 21 */
+  int32_t min_interval_size;          /* 13 */
+  int32_t approved_interval_number;   /* 20 */
+  int32_t max_process_intervals;      /* 4 */
+  int32_t min_read_length_after_chop; /* 20 */
+  int32_t min_read_length;            /* 150 = MIN_READ_LEN; 0 disables the gate (PyO3 smooth_label_region) */
+  int32_t chop_type;                  /* DCB200_CHOP_* */
+  int32_t output_chopped_seqs;        /* --ocq */
+} dcb200_chop_params;
+
+const char* dcb200_last_error(void);
+int dcb200_version(void);
+void dcb200_chop_params_default(dcb200_chop_params* p);
+
+/* ctx: stream == NULL -> the ctx creates (and owns) a non-blocking stream; otherwise the given
+ * cudaStream_t is used (e.g. torch.cuda.current_stream().cuda_stream). */
+int dcb200_ctx_create(int device, void* stream, dcb200_ctx** out);
+int dcb200_ctx_destroy(dcb200_ctx* ctx);
+int dcb200_ctx_sync(dcb200_ctx* ctx);
+void* dcb200_ctx_stream(dcb200_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t dcb200_ctx_launch_count(dcb200_ctx* ctx);
+
+/* ---- FASTQ -> tokens + L2-normalised quality --------------------------------------------------
+ * bytes: device-accessible FASTQ text (or any byte buffer holding seq and quality strings);
+ * seq_off/qual_off[R]: byte offsets of each read's sequence / quality string, len[R]: bases kept
+ * (already truncated to max_tokens-1 by the caller, tokenizer.py:154-163); Lpad >= max(len)+1.
+ * Row r of tok/qual is LEFT padded: [PAD(4)...][bases][SEP(1)], qual 0 at pads and SEP. */
+int dcb200_encode_batch(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
+                        const int32_t* len, int32_t R, int32_t Lpad, uint8_t* tok, float* qual);
+
+/* ---- weights ------------------------------------------------------------------------------------
+ * State dict as parallel arrays of names / host fp32 pointers / element counts.  Names are the
+ * reference's keys ("net.backbone.backbone.layers.0.mixer.in_linear.weight", ...; any prefix before
+ * "embeddings." / "layers." / "ln_f." / "head." is ignored).  Converts to the device layouts and
+ * evaluates the implicit long-conv filters k[layer][256][max_seq_len] once. */
+int dcb200_weights_create(dcb200_ctx* ctx, const char* const* names, const float* const* data, const int64_t* numel,
+                          int32_t n_tensors, dcb200_weights** out);
+int dcb200_weights_destroy(dcb200_weights* w);
+
+/* ---- model forward ------------------------------------------------------------------------------
+ * tok [B,L] u8, qual [B,L] f32 (device).  L must be a multiple of 128 and <= 32768.
+ * logits [B,L,2] f32 and/or labels [B,L] u8 (label = logit1 > logit0) may be NULL. */
+int dcb200_forward(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B,
+                   int32_t L, float* logits, uint8_t* labels);
+
+/* ---- smoothing / intervals / chop coordinates ------------------------------------------------------
+ * labels: device int8 buffer of labels_bytes bytes; read r occupies labels[starts[r] .. +lens[r]).
+ * qual_lens (device, may be NULL): FASTQ quality length per read; != lens[r] means the prediction
+ * was truncated -> passthrough (src/bin/predict.rs:160-164).
+ * Outputs (device): n_adapter[R], adapter_iv[R][approved][2], n_keep[R], keep_iv[R][approved+1][2],
+ * action[R].  Only the first n_* entries of a row are written. */
+int dcb200_smooth_chop(dcb200_ctx* ctx, const int8_t* labels, int64_t labels_bytes, const int64_t* starts,
+                       const int32_t* lens, const int32_t* qual_lens, int64_t R, const dcb200_chop_params* p,
+                       int32_t* n_adapter, int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv, uint8_t* action);
+
+/* Same, reading fp32 logits [n_tokens][2] instead of labels: label = logit1 > logit0 (argmax, ties
+ * -> class 0); starts/lens index tokens. */
+int dcb200_smooth_chop_logits(dcb200_ctx* ctx, const float* logits, int64_t n_tokens, const int64_t* starts,
+                              const int32_t* lens, const int32_t* qual_lens, int64_t R, const dcb200_chop_params* p,
+                              int32_t* n_adapter, int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv,
+                              uint8_t* action);
+
+/* majority_voting over R reads; out has the layout of labels (only read positions are written). */
+int dcb200_majority_voting(dcb200_ctx* ctx, const int8_t* labels, int64_t labels_bytes, const int64_t* starts,
+                           const int32_t* lens, int64_t R, int32_t window, int8_t* out);
+
+/* Host-buffer convenience forms: copy in, run, copy out, synchronise. */
+int dcb200_smooth_chop_host(dcb200_ctx* ctx, const int8_t* labels, int64_t labels_bytes, const int64_t* starts,
+                            const int32_t* lens, const int32_t* qual_lens, int64_t R, const dcb200_chop_params* p,
+                            int32_t* n_adapter, int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv,
+                            uint8_t* action);
+int dcb200_majority_voting_host(dcb200_ctx* ctx, const int8_t* labels, int64_t labels_bytes, const int64_t* starts,
+                                const int32_t* lens, int64_t R, int32_t window, int8_t* out);
+
+/* ---- whole hot loop on host buffers ----------------------------------------------------------------
+ * One batch of R reads out of a (pinned) host FASTQ buffer: H2D -> encode -> forward -> smooth/chop
+ * -> D2H, synchronised on return.  logits_out [R,Lpad,2] / labels_out [R,Lpad] (host) may be NULL;
+ * interval outputs (host) as in dcb200_smooth_chop.  qual_lens may be NULL. */
+int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
+                              const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
+                              const int32_t* qual_lens, int32_t R, int32_t Lpad, const dcb200_chop_params* p,
+                              float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
+                              int32_t* n_keep, int32_t* keep_iv, uint8_t* action);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB200_H_ */

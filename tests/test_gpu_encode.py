@@ -1,0 +1,50 @@
+"""-m gpu parity of the FASTQ -> token / normalised-quality encoder against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hyena_ref as H
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode(recs, Lpad):
+    from deepchopper_b200 import encode
+    return encode.encode_records(recs, Lpad)
+
+
+def test_encode_matches_oracle(dcref):
+    rng = np.random.default_rng(3)
+    recs = synth.fastq_reads(rng, 64, 1, 700)
+    recs.append(("lower", "acgtnACGTNuUxX.-~", "!" * 17))          # case fold, U->T, exotic -> N / UNK
+    recs.append(("allzero", "ACGT", "!!!!"))                        # zero norm -> eps clamp, quals stay 0
+    recs.append(("one", "A", "I"))
+    Lpad = 768
+    tok, qual = _encode(recs, Lpad)
+    tok, qual = tok.cpu().numpy(), qual.cpu().numpy()
+    for r, (rid, s, q) in enumerate(recs):
+        t_ref, q_ref = dcref.encode_read(s.encode(), q.encode(), Lpad)
+        assert np.array_equal(tok[r], t_ref), rid
+        assert np.array_equal(qual[r], q_ref), rid                  # bit-exact vs the C oracle (exact integer norm)
+        # and against the torch restatement of tokenizer.py:145-178 within fp32 rounding of the norm
+        feat = H.tokenize_read(rid, s, q)
+        b = H.collate([feat], pad_to=Lpad)
+        assert np.array_equal(tok[r], b["input_ids"][0].numpy().astype(np.uint8)), rid
+        np.testing.assert_allclose(qual[r], b["input_quals"][0].numpy(), rtol=1e-6, atol=1e-9)
+
+
+def test_encode_rows_unit_norm_full_size():
+    rng = np.random.default_rng(4)
+    lens = synth.read_lengths(rng, 4096)
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    Lpad = int((lens.max() + 1 + 127) // 128 * 128)
+    tok, qual = _encode(recs, Lpad)
+    nrm = qual.double().pow(2).sum(1).sqrt().cpu().numpy()
+    np.testing.assert_allclose(nrm, 1.0, atol=1e-5)
+    tok = tok.cpu().numpy()
+    assert (tok[:, -1] == 1).all()
+    first = (tok != 4).argmax(1)
+    assert np.array_equal(Lpad - first - 1, lens)

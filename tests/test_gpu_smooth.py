@@ -1,0 +1,155 @@
+"""-m gpu parity tests of the smoothing / interval / chop-coordinate kernel against the oracle,
+through the C ABI (dcb200_smooth_chop*, dcb200_majority_voting*)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import smooth_ref as S
+from tests import synth
+from tests.test_oracle_smooth import MV_KATS, REGION_KATS, _random_labels
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def sm():
+    from deepchopper_b200 import smooth
+    return smooth
+
+
+@pytest.mark.parametrize("labels,window,expected", MV_KATS)
+def test_majority_voting_kats(sm, labels, window, expected):
+    assert sm.majority_voting(labels, window) == expected
+
+
+@pytest.mark.parametrize("labels,expected", REGION_KATS)
+def test_get_label_region_kats(sm, labels, expected):
+    assert sm.get_label_region(labels) == expected
+
+
+def test_predict_class_surface(sm):
+    lab = [0] * 50 + [1] * 40 + [0] * 100 + [1] * 5 + [0] * 30
+    p = sm.Predict(lab, "A" * len(lab), "x", False)
+    o = S.Predict(lab, "A" * len(lab), "x")
+    assert p.prediction_region() == o.prediction_region()
+    assert p.smooth_prediction(21) == o.smooth_prediction(21)
+    assert p.smooth_label(21) == o.smooth_label(21)
+    assert p.smooth_and_select_intervals(21, 13, 20) == o.smooth_and_select_intervals(21, 13, 20)
+    assert p.seq_len() == len(lab)
+
+
+def test_fixture72_bit_exact(sm, dcref):
+    z = np.load(os.path.join(GOLD, "smooth_fixture.npz"))
+    meta = json.load(open(os.path.join(GOLD, "smooth_fixture.json")))
+    offs = z["offsets"]
+    lens = np.diff(offs).astype(np.int32)
+    res = sm.smooth_chop_host(z["labels"], offs[:-1], lens)
+    ref = dcref.smooth_chop(z["labels"], offs[:-1], lens)
+    for r in range(lens.size):
+        want = [tuple(x) for x in meta["intervals"][r]]
+        if lens[r] >= 150:
+            assert res.adapters(r) == want, meta["ids"][r]
+    for k in ("n_adapter", "n_keep", "action"):
+        assert np.array_equal(getattr(res, k), ref[k]), k
+    for r in range(lens.size):
+        assert np.array_equal(res.adapter_iv[r, :res.n_adapter[r]], ref["adapter_iv"][r, :ref["n_adapter"][r]])
+        assert np.array_equal(res.keep_iv[r, :res.n_keep[r]], ref["keep_iv"][r, :ref["n_keep"][r]])
+
+
+def _compare(res, ref):
+    for k in ("n_adapter", "n_keep", "action"):
+        bad = np.nonzero(getattr(res, k) != ref[k])[0]
+        assert bad.size == 0, (k, bad[:10], getattr(res, k)[bad[:10]], ref[k][bad[:10]])
+    ap = res.adapter_iv.shape[1]
+    m = np.arange(ap)[None, :] < res.n_adapter[:, None]
+    assert np.array_equal(res.adapter_iv[m], ref["adapter_iv"][m])
+    m = np.arange(ap + 1)[None, :] < res.n_keep[:, None]
+    assert np.array_equal(res.keep_iv[m], ref["keep_iv"][m])
+
+
+PARAM_SETS = [
+    dict(window=21, min_interval=13, approved=20, max_process=4, min_after_chop=20, min_read_len=150, chop_type=2, ocq=0),
+    dict(window=21, min_interval=13, approved=20, max_process=4, min_after_chop=20, min_read_len=150, chop_type=0, ocq=0),
+    dict(window=21, min_interval=13, approved=20, max_process=4, min_after_chop=20, min_read_len=150, chop_type=1, ocq=0),
+    dict(window=21, min_interval=13, approved=20, max_process=4, min_after_chop=20, min_read_len=150, chop_type=2, ocq=1),
+    dict(window=1, min_interval=0, approved=64, max_process=64, min_after_chop=0, min_read_len=0, chop_type=2, ocq=0),
+    dict(window=2, min_interval=2, approved=1, max_process=1, min_after_chop=50, min_read_len=20, chop_type=2, ocq=0),
+    dict(window=11, min_interval=5, approved=3, max_process=2, min_after_chop=10, min_read_len=0, chop_type=0, ocq=0),
+    dict(window=51, min_interval=13, approved=20, max_process=4, min_after_chop=20, min_read_len=150, chop_type=2, ocq=0),
+    dict(window=63, min_interval=1, approved=20, max_process=20, min_after_chop=1, min_read_len=0, chop_type=2, ocq=0),
+    dict(window=101, min_interval=13, approved=20, max_process=4, min_after_chop=20, min_read_len=0, chop_type=2, ocq=0),
+]
+
+
+@pytest.mark.parametrize("ps", PARAM_SETS)
+def test_random_ragged_reads_bit_exact(sm, dcref, ps):
+    from deepchopper_b200 import ChopParams
+    rng = np.random.default_rng(11)
+    lens = np.concatenate([rng.integers(0, 70, 300), rng.integers(100, 3000, 300), [0, 1, 2, 31, 32, 33, 1023, 1024, 1025, 2047, 2048, 2049, 8192]])
+    labs = [_random_labels(rng, int(n)) if n else np.zeros(0, np.int8) for n in lens]
+    # unaligned starts: put a random gap in front of every read
+    gaps = rng.integers(0, 37, lens.size)
+    starts = np.cumsum(gaps + np.concatenate([[0], lens[:-1]])).astype(np.int64)
+    buf = (rng.random(int(starts[-1] + lens[-1] + 5)) < 0.5).astype(np.int8)  # junk between reads must not leak in
+    for s, l in zip(starts, labs):
+        buf[s:s + l.size] = l
+    qual_lens = lens.astype(np.int32).copy()
+    qual_lens[::13] += 3
+    p = ChopParams.default(smooth_window_size=ps["window"], min_interval_size=ps["min_interval"],
+                           approved_interval_number=ps["approved"], max_process_intervals=ps["max_process"],
+                           min_read_length_after_chop=ps["min_after_chop"], min_read_length=ps["min_read_len"],
+                           chop_type=ps["chop_type"], output_chopped_seqs=ps["ocq"])
+    res = sm.smooth_chop_host(buf, starts, lens.astype(np.int32), p, qual_lens)
+    ref = dcref.smooth_chop(buf, starts, lens.astype(np.int32), qual_lens, **ps)
+    _compare(res, ref)
+    sm_gpu = sm.majority_voting_host(buf, starts, lens.astype(np.int32), ps["window"])
+    for s, l in zip(starts[::7], labs[::7]):
+        assert np.array_equal(sm_gpu[s:s + l.size], dcref.majority_voting(l, ps["window"]))
+
+
+def test_logits_variant_matches_label_variant(sm):
+    import torch
+    from deepchopper_b200 import ChopParams
+    rng = np.random.default_rng(5)
+    lens = synth.read_lengths(rng, 500)
+    lab, starts, lens32 = synth.planted_labels(rng, lens)
+    margin = rng.random(lab.size).astype(np.float32) + 0.01
+    logits = np.stack([np.where(lab == 1, 0, margin), np.where(lab == 1, margin, 0)], 1).astype(np.float32)
+    logits[::97] = 0.5   # exact ties -> class 0 (argmax first index)
+    lab2 = (logits[:, 1] > logits[:, 0]).astype(np.int8)
+    a = sm.smooth_chop_device(torch.from_numpy(lab2).cuda(), torch.from_numpy(starts).cuda(), torch.from_numpy(lens32).cuda())
+    b = sm.smooth_chop_device(torch.from_numpy(logits).cuda(), torch.from_numpy(starts).cuda(), torch.from_numpy(lens32).cuda(), logits=True)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_full_size_properties(sm, dcref):
+    """BASELINE config-5 sized slice (2M reads here; 10M in bench) through size-independent properties:
+    idempotent action histogram vs a 20k-read oracle sample, interval sanity on everything."""
+    import torch
+    rng = np.random.default_rng(2026)
+    lens = synth.read_lengths(rng, 2_000_000)
+    lab, starts, lens32 = synth.planted_labels_fast(rng, lens)
+    n_ad, ad, n_keep, keep, act = [t.cpu().numpy() for t in sm.smooth_chop_device(
+        torch.from_numpy(lab).cuda(), torch.from_numpy(starts).cuda(), torch.from_numpy(lens32).cuda())]
+    # properties: intervals sorted, disjoint, inside the read, long enough; kept pieces complement adapters
+    m = np.arange(20)[None, :] < n_ad[:, None]
+    s, e = ad[..., 0], ad[..., 1]
+    assert (e[m] - s[m] >= 13).all() and (s[m] >= 1).all()
+    assert (e[m] <= np.broadcast_to(lens32[:, None], e.shape)[m]).all()
+    m2 = m[:, 1:] & m[:, :-1]
+    assert (s[:, 1:][m2] > e[:, :-1][m2]).all()
+    assert ((act == 0) | (n_keep > 0) | (n_ad > 0)).all()
+    # exact agreement with the oracle on a sample
+    idx = rng.choice(lens.size, 20000, replace=False)
+    ref = dcref.smooth_chop(lab, starts[idx], lens32[idx])
+    assert np.array_equal(n_ad[idx], ref["n_adapter"]) and np.array_equal(act[idx], ref["action"])
+    assert np.array_equal(n_keep[idx], ref["n_keep"])
+    mm = np.arange(20)[None, :] < ref["n_adapter"][:, None]
+    assert np.array_equal(ad[idx][mm], ref["adapter_iv"][mm])
+    mk = np.arange(21)[None, :] < ref["n_keep"][:, None]
+    assert np.array_equal(keep[idx][mk], ref["keep_iv"][mk])
