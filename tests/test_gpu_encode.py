@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import hyena_ref as H
-from tests import synth
+from deepchopper_b200 import synth
 
 pytestmark = pytest.mark.gpu
 

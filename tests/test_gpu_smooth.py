@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import smooth_ref as S
-from tests import synth
-from tests.test_oracle_smooth import MV_KATS, REGION_KATS, _random_labels
+from deepchopper_b200 import synth
+from helpers_kats import MV_KATS, REGION_KATS, _random_labels
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")

@@ -10,24 +10,7 @@ from oracle import smooth_ref as S
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
-# ---- majority_voting: src/smooth/utils.rs:103-137 --------------------------------------------
-MV_KATS = [
-    ([1, 0, 0, 1, 1, 0, 1, 0, 0, 0, 1], 3, [1, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0]),
-    ([1, 0, 0, 1, 1, 0, 1, 1, 1, 0, 1], 3, [1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1]),
-    ([], 3, []),
-    ([1, 0, 0, 1, 1, 0, 1, 0, 0, 0], 1, [1, 0, 0, 1, 1, 0, 1, 0, 0, 0]),
-]
-# ---- get_label_region: src/utils.rs:770-803 (+ derived start==0 quirk cases) ------
-REGION_KATS = [
-    ([], []),
-    ([0, 0, 0, 0], []),
-    ([0, 1, 0, 0, 0], [(1, 2)]),
-    ([0, 1, 1, 0, 1, 1, 0], [(1, 3), (4, 6)]),
-    ([0, 1, 1, 0, 1, 1], [(1, 3), (4, 6)]),
-    ([1, 1, 1, 0], [(1, 3)]),
-    ([1, 0, 0], []),
-    ([1], []),
-]
+from helpers_kats import MV_KATS, REGION_KATS, _random_labels  # noqa: E402
 
 
 @pytest.mark.parametrize("labels,window,expected", MV_KATS)
@@ -135,21 +118,6 @@ def test_c_oracle_batch_equals_python_on_fixture(fixture72, dcref):
                 assert [tuple(x) for x in res["adapter_iv"][r][:len(ad)]] == ad
                 assert res["n_keep"][r] == len(keep)
                 assert [tuple(x) for x in res["keep_iv"][r][:len(keep)]] == keep
-
-
-def _random_labels(rng, n):
-    lab = (rng.random(n) < 0.03).astype(np.int8)
-    for _ in range(rng.integers(0, 5)):
-        if n < 4:
-            break
-        s = int(rng.integers(0, n))
-        e = min(n, s + int(rng.integers(5, 120)))
-        lab[s:e] = (rng.random(e - s) > 0.08)
-    if rng.random() < 0.3:
-        lab[: int(rng.integers(1, 40))] = 1
-    if rng.random() < 0.5:
-        lab[n - int(rng.integers(1, 80)):] = 1
-    return lab
 
 
 def test_c_oracle_equals_python_random():
