@@ -13,6 +13,7 @@ EXPORTS = [
     "dcb200_ctx_sync", "dcb200_ctx_stream", "dcb200_ctx_launch_count", "dcb200_encode_batch", "dcb200_weights_create",
     "dcb200_weights_destroy", "dcb200_forward", "dcb200_smooth_chop", "dcb200_smooth_chop_logits",
     "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
+    "dcb200_forward_debug", "dcb200_ctx_read_workspace",
 ]
 
 
@@ -58,10 +59,12 @@ def lib():
     l.dcb200_ctx_stream.restype = vp
     l.dcb200_ctx_launch_count.argtypes = [vp]
     l.dcb200_ctx_launch_count.restype = i64
-    l.dcb200_encode_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    l.dcb200_encode_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     l.dcb200_weights_create.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(vp)]
     l.dcb200_weights_destroy.argtypes = [vp]
     l.dcb200_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    l.dcb200_forward_debug.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i32]
+    l.dcb200_ctx_read_workspace.argtypes = [vp, C.c_char_p, vp, i64]
     pp = C.POINTER(ChopParams)
     l.dcb200_smooth_chop.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_smooth_chop_logits.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]

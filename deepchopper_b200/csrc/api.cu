@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
-                  const int32_t* len, int32_t R, int32_t Lpad, uint8_t* tok, float* qual);
+                  const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual);
 int smooth_chop_device(dcb200_ctx* ctx, const int8_t* labels, const float* logits, int64_t total, const int64_t* starts,
                        const int32_t* lens, const int32_t* qual_lens, int64_t R, const dcb200_chop_params* p,
                        int32_t* n_adapter, int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv, uint8_t* action,
@@ -24,7 +24,7 @@ int weights_create(dcb200_ctx* ctx, const char* const* names, const float* const
                    int32_t n, dcb200_weights** out);
 int weights_destroy(dcb200_weights* w);
 int forward_device(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
-                   float* logits, uint8_t* labels);
+                   float* logits, uint8_t* labels, int stop_stage);
 
 static int check_params(const dcb200_chop_params* p) {
   DCB_ARG(p != nullptr);
@@ -114,12 +114,12 @@ void* dcb200_ctx_stream(dcb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nul
 int64_t dcb200_ctx_launch_count(dcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int dcb200_encode_batch(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
-                        const int32_t* len, int32_t R, int32_t Lpad, uint8_t* tok, float* qual) {
+                        const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual) {
   DCB_ARG(ctx && bytes && seq_off && qual_off && len && tok && qual);
-  DCB_ARG(R >= 0 && Lpad > 0 && Lpad % 4 == 0);
+  DCB_ARG(R >= 0 && Lpad > 0 && Lrow >= Lpad && Lrow % 4 == 0);
   DCB_ARG((reinterpret_cast<uintptr_t>(tok) & 3) == 0 && (reinterpret_cast<uintptr_t>(qual) & 15) == 0);
   DCB_CUDA(cudaSetDevice(ctx->device));
-  return encode_device(ctx, bytes, seq_off, qual_off, len, R, Lpad, tok, qual);
+  return encode_device(ctx, bytes, seq_off, qual_off, len, R, Lpad, Lrow, tok, qual);
 }
 
 int dcb200_weights_create(dcb200_ctx* ctx, const char* const* names, const float* const* data, const int64_t* numel,
@@ -136,7 +136,30 @@ int dcb200_forward(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok,
   DCB_ARG(ctx && w && tok && qual);
   DCB_ARG(B > 0 && L > 0 && L % 128 == 0 && L <= 32768);
   DCB_CUDA(cudaSetDevice(ctx->device));
-  return forward_device(ctx, w, tok, qual, B, L, logits, labels);
+  return forward_device(ctx, w, tok, qual, B, L, logits, labels, 1 << 30);
+}
+
+int dcb200_forward_debug(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B,
+                         int32_t L, float* logits, uint8_t* labels, int32_t stop_stage) {
+  DCB_ARG(ctx && w && tok && qual);
+  DCB_ARG(B > 0 && L > 0 && L % 128 == 0 && L <= 32768);
+  DCB_CUDA(cudaSetDevice(ctx->device));
+  DCB_CHECK(forward_device(ctx, w, tok, qual, B, L, logits, labels, stop_stage));
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DCB200_OK;
+}
+
+int dcb200_ctx_read_workspace(dcb200_ctx* ctx, const char* name, void* host_dst, int64_t bytes) {
+  DCB_ARG(ctx && name && host_dst && bytes >= 0);
+  DCB_CUDA(cudaSetDevice(ctx->device));
+  auto it = ctx->ws.find(name);
+  if (it == ctx->ws.end() || (size_t)bytes > it->second.cap) {
+    set_error("workspace '%s' missing or smaller than %lld bytes", name, (long long)bytes);
+    return DCB200_EINVAL;
+  }
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  DCB_CUDA(cudaMemcpy(host_dst, it->second.p, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return DCB200_OK;
 }
 
 int dcb200_smooth_chop(dcb200_ctx* ctx, const int8_t* labels, int64_t labels_bytes, const int64_t* starts,
@@ -253,11 +276,12 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
                               float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
                               int32_t* n_keep, int32_t* keep_iv, uint8_t* action) {
   DCB_ARG(ctx && w && bytes && seq_off && qual_off && len && n_adapter && adapter_iv && n_keep && keep_iv && action);
-  DCB_ARG(R > 0 && n_bytes > 0 && Lpad > 0 && Lpad % 128 == 0 && Lpad <= 32768);
+  DCB_ARG(R > 0 && n_bytes > 0 && Lpad > 0 && Lpad <= 32768);
   DCB_CHECK(check_params(p));
   DCB_CUDA(cudaSetDevice(ctx->device));
   const int ap = p->approved_interval_number;
-  const size_t T = (size_t)R * Lpad;
+  const int Lrow = (Lpad + 127) / 128 * 128;  // row stride; columns >= Lpad are inert right filler (causal model)
+  const size_t T = (size_t)R * Lrow;
   void *d_bytes, *d_so, *d_qo, *d_len, *d_ql = nullptr, *d_tok, *d_q, *d_lab, *d_logits = nullptr, *d_st;
   void *d_na, *d_ad, *d_nk, *d_kp, *d_act;
   DCB_CHECK(stage_in(ctx, "p_bytes", bytes, (size_t)n_bytes, &d_bytes));
@@ -269,7 +293,7 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   std::vector<int64_t> st(R);
   for (int r = 0; r < R; ++r) {
     DCB_ARG(len[r] >= 0 && len[r] + 1 <= Lpad);
-    st[r] = (int64_t)r * Lpad + (Lpad - 1 - len[r]);
+    st[r] = (int64_t)r * Lrow + (Lpad - 1 - len[r]);
   }
   DCB_CHECK(stage_in(ctx, "p_starts", st.data(), (size_t)R * 8, &d_st));
   DCB_CHECK(stage_out(ctx, "p_tok", T, &d_tok));
@@ -286,13 +310,17 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   DCB_CUDA(cudaMemsetAsync(d_ad, 0, (size_t)R * ap * 8, ctx->stream));
   DCB_CUDA(cudaMemsetAsync(d_kp, 0, (size_t)R * (ap + 1) * 8, ctx->stream));
   DCB_CHECK(encode_device(ctx, (const uint8_t*)d_bytes, (const int64_t*)d_so, (const int64_t*)d_qo, (const int32_t*)d_len, R,
-                          Lpad, (uint8_t*)d_tok, (float*)d_q));
-  DCB_CHECK(forward_device(ctx, w, (const uint8_t*)d_tok, (const float*)d_q, R, Lpad, (float*)d_logits, (uint8_t*)d_lab));
+                          Lpad, Lrow, (uint8_t*)d_tok, (float*)d_q));
+  DCB_CHECK(forward_device(ctx, w, (const uint8_t*)d_tok, (const float*)d_q, R, Lrow, (float*)d_logits, (uint8_t*)d_lab, 1 << 30));
   DCB_CHECK(smooth_chop_device(ctx, (const int8_t*)d_lab, nullptr, (int64_t)T, (const int64_t*)d_st, (const int32_t*)d_len,
                                (const int32_t*)d_ql, R, p, (int32_t*)d_na, (int32_t*)d_ad, (int32_t*)d_nk, (int32_t*)d_kp,
                                (uint8_t*)d_act, nullptr));
-  if (logits_out) DCB_CUDA(cudaMemcpyAsync(logits_out, d_logits, T * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (labels_out) DCB_CUDA(cudaMemcpyAsync(labels_out, d_lab, T, cudaMemcpyDeviceToHost, ctx->stream));
+  if (logits_out)
+    DCB_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)Lpad * 8, d_logits, (size_t)Lrow * 8, (size_t)Lpad * 8, R,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  if (labels_out)
+    DCB_CUDA(cudaMemcpy2DAsync(labels_out, (size_t)Lpad, d_lab, (size_t)Lrow, (size_t)Lpad, R, cudaMemcpyDeviceToHost,
+                               ctx->stream));
   DCB_CUDA(cudaMemcpyAsync(n_adapter, d_na, (size_t)R * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (ap) DCB_CUDA(cudaMemcpyAsync(adapter_iv, d_ad, (size_t)R * ap * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DCB_CUDA(cudaMemcpyAsync(n_keep, d_nk, (size_t)R * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -30,8 +30,8 @@ __device__ __forceinline__ uint32_t base_to_token(uint32_t c) {
 
 __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ seq_off,
                                                      const int64_t* __restrict__ qual_off, const int32_t* __restrict__ len,
-                                                     int32_t R, int32_t Lpad, uint8_t* __restrict__ tok,
-                                                     float* __restrict__ qual) {
+                                                     int32_t R, int32_t Lpad, int32_t Lrow,
+                                                     uint8_t* __restrict__ tok, float* __restrict__ qual) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__
     float nrm = sqrtf((float)acc);               // F.normalize: x / max(||x||_2, eps), tokenizer.py:167
     nrm = fmaxf(nrm, 1e-12f);
     const int pad = Lpad - (n + 1);
-    uint32_t* trow = reinterpret_cast<uint32_t*>(tok + (int64_t)r * Lpad);
-    float4* qrow = reinterpret_cast<float4*>(qual + (int64_t)r * Lpad);
-    for (int c4 = lane; c4 < Lpad / 4; c4 += 32) {
+    uint32_t* trow = reinterpret_cast<uint32_t*>(tok + (int64_t)r * Lrow);
+    float4* qrow = reinterpret_cast<float4*>(qual + (int64_t)r * Lrow);
+    for (int c4 = lane; c4 < Lrow / 4; c4 += 32) {
       uint32_t tw = 0;
       float qv[4];
 #pragma unroll
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__
         const int i = col - pad;
         uint32_t t;
         float f = 0.0f;
-        if (i < 0) t = DCB200_TOK_PAD;
+        if (i < 0 || i > n) t = DCB200_TOK_PAD;  // left pad (semantic) / right filler up to the row stride (causal model: inert)
         else if (i == n) t = DCB200_TOK_SEP;
         else {
           t = base_to_token(s[i]);
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__
 }
 
 int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
-                  const int32_t* len, int32_t R, int32_t Lpad, uint8_t* tok, float* qual) {
+                  const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual) {
   if (R == 0) return DCB200_OK;
   const int threads = 256;
   int blocks = (R + 7) / 8;
   const int cap = ctx->sm_count * 8 * 4;
   if (blocks > cap) blocks = cap;
-  encode_kernel<<<blocks, threads, 0, ctx->stream>>>(bytes, seq_off, qual_off, len, R, Lpad, tok, qual);
+  encode_kernel<<<blocks, threads, 0, ctx->stream>>>(bytes, seq_off, qual_off, len, R, Lpad, Lrow, tok, qual);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }

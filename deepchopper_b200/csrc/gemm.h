@@ -1,0 +1,34 @@
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+struct dcb200_ctx;
+
+namespace dcb {
+
+enum GemmMode { G_INPROJ = 0, G_OUTPROJ = 1, G_FC1 = 2, G_FC2 = 3, G_HEAD1 = 4, G_HEAD2 = 5 };
+
+struct GemmParams {
+  int T;          // tokens = B * L (multiple of 128)
+  int L;          // padded read length (multiple of 128)
+  int num_outer;  // T / 128 token tiles
+  const float* bias;
+  const float* resid;       // fp32 [T,256]          (OUTPROJ, FC2)
+  float* h_out;             // fp32 [T,256] or null  (OUTPROJ, FC2)
+  const float* ln_g;        // [256]
+  const float* ln_b;        // [256]
+  __nv_bfloat16* out_bf16;  // INPROJ: z [B,768,L]; OUTPROJ/FC2: u [T,256]; FC1: g [T,1024]; HEAD1: r [T,1024]
+  const float* qual;        // HEAD1: [T]
+  const __nv_bfloat16* r_in;  // HEAD2: r [T,1024]
+  const float* w3;          // HEAD2: [2,1024]
+  const float* b3;          // HEAD2: [2]
+  float* logits;            // HEAD2: [T,2] or null
+  uint8_t* labels;          // HEAD2: [T] or null
+};
+
+int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p);
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int make_tmap_3d_cm(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L);
+
+}  // namespace dcb

@@ -1,13 +1,435 @@
+// Weights + forward orchestration of the HyenaDNA-small-32k token classifier:
+//   embedding -> 4 x [LN1 -> in_proj -> short conv/gate/long conv/gate -> out_proj + res -> LN2 -> MLP + res]
+//   -> ln_f -> head (deepchopper/models/llm/head.py:94-102) -> logits / labels
+// Reference entry: deepchopper/models/basic_module.py:90-100 -> deepchopper/models/llm/hyena.py:29-41.
 #include "common.cuh"
-struct dcb200_weights { int dummy; };
+#include "fftconv.h"
+#include "gemm.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
 namespace dcb {
-int weights_create(dcb200_ctx*, const char* const*, const float* const*, const int64_t*, int32_t, dcb200_weights**) {
-  set_error("model path not built yet");
-  return DCB200_EWEIGHT;
+
+constexpr int kD = 256;
+constexpr int kLayers = 4;
+constexpr int kInner = 1024;
+constexpr int kFilterOrder = 64;
+constexpr int kEmbDim = 5;
+constexpr int kVocab = 16;
+
+struct LayerW {
+  __nv_bfloat16 *w_in = nullptr, *w_out = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
+  float *b_in = nullptr, *b_out = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
+  float *short_w = nullptr, *short_b = nullptr, *filt_D = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  float* k = nullptr;  // [256][Lmax] implicit filter, evaluated once
+  std::map<int, float2*> KF;  // per FFT size N: [256][N]
+  CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
+};
+
+}  // namespace dcb
+
+struct dcb200_weights {
+  int device = 0;
+  int Lmax = 0;
+  float* emb = nullptr;  // [16][256]
+  dcb::LayerW layer[dcb::kLayers];
+  float *lnf_g = nullptr, *lnf_b = nullptr;
+  __nv_bfloat16 *wh1 = nullptr, *wh2 = nullptr;
+  float *bh1 = nullptr, *bh2 = nullptr, *w3 = nullptr, *b3 = nullptr;
+  CUtensorMap tm_h1, tm_h2;
+  std::map<int, float2*> tw;  // per FFT size N: exp(-2 pi i k/N)
+  std::vector<void*> allocs;
+};
+
+namespace dcb {
+
+// ---- small kernels --------------------------------------------------------------------------------
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
-int weights_destroy(dcb200_weights* w) { delete w; return DCB200_OK; }
-int forward_device(dcb200_ctx*, const dcb200_weights*, const uint8_t*, const float*, int32_t, int32_t, float*, uint8_t*) {
-  set_error("model path not built yet");
-  return DCB200_EINVAL;
+
+// Implicit filter MLP (modeling_hyena.py HyenaFilter.filter): one thread per position t.
+//   h = Lin6( sin(f5 * Lin4( sin(f3 * Lin2( sin(f1 * Lin0(z_t)) )) )) ),  k[c][t] = h_c * (exp(-t |delta_c|) + 0.05)
+struct FilterW {
+  const float *z, *t;              // [Lmax,5], [Lmax]
+  const float *w0, *b0, *f1;       // [64,5], [64], [64]
+  const float *w2, *b2, *f3;       // [64,64], [64], [64]
+  const float *w4, *b4, *f5;       // [64,64], [64], [64]
+  const float *w6;                 // [256,64]
+  const float *deltas;             // [256]
+};
+
+__global__ void __launch_bounds__(128) implicit_filter_kernel(FilterW w, int Lmax, float* __restrict__ k) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Lmax) return;
+  float h1[kFilterOrder], h2[kFilterOrder];
+  float zt[kEmbDim];
+  for (int i = 0; i < kEmbDim; ++i) zt[i] = w.z[(size_t)t * kEmbDim + i];
+  for (int j = 0; j < kFilterOrder; ++j) {
+    float a = w.b0[j];
+    for (int i = 0; i < kEmbDim; ++i) a = fmaf(w.w0[j * kEmbDim + i], zt[i], a);
+    h1[j] = sinf(w.f1[j] * a);
+  }
+  for (int j = 0; j < kFilterOrder; ++j) {
+    float a = w.b2[j];
+    for (int i = 0; i < kFilterOrder; ++i) a = fmaf(w.w2[j * kFilterOrder + i], h1[i], a);
+    h2[j] = sinf(w.f3[j] * a);
+  }
+  for (int j = 0; j < kFilterOrder; ++j) {
+    float a = w.b4[j];
+    for (int i = 0; i < kFilterOrder; ++i) a = fmaf(w.w4[j * kFilterOrder + i], h2[i], a);
+    h1[j] = sinf(w.f5[j] * a);
+  }
+  const float tt = w.t[t];
+  for (int c = 0; c < kD; ++c) {
+    float a = 0.f;
+    for (int i = 0; i < kFilterOrder; ++i) a = fmaf(w.w6[c * kFilterOrder + i], h1[i], a);
+    k[(size_t)c * Lmax + t] = a * (expf(-tt * fabsf(w.deltas[c])) + 0.05f);
+  }
 }
+
+__global__ void twiddle_kernel(float2* tw, int N) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  double s, c;
+  sincospi(2.0 * (double)k / (double)N, &s, &c);
+  tw[k] = make_float2((float)c, (float)(-s));
 }
+
+// Embedding gather + LayerNorm1 of layer 0: one warp per token (8 features per lane).
+__global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict__ tok, const float* __restrict__ emb,
+                                                       const float* __restrict__ g, const float* __restrict__ b, int T,
+                                                       float* __restrict__ h, __nv_bfloat16* __restrict__ u) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int t = warp; t < T; t += nwarps) {
+    int id = tok[t];
+    id = id < kVocab ? id : kVocab - 1;
+    const float4* e4 = reinterpret_cast<const float4*>(emb + id * kD + lane * 8);
+    const float4 a = __ldg(e4), c = __ldg(e4 + 1);
+    float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    const float mean = s * (1.0f / kD);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v = fmaf(x[i] - mean, x[i] - mean, v);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const float rstd = rsqrtf(v * (1.0f / kD) + 1e-5f);
+    float4* h4 = reinterpret_cast<float4*>(h + (size_t)t * kD + lane * 8);
+    h4[0] = a;
+    h4[1] = c;
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = lane * 8 + 2 * i;
+      const float y0 = fmaf((x[2 * i] - mean) * rstd, __ldg(g + col), __ldg(b + col));
+      const float y1 = fmaf((x[2 * i + 1] - mean) * rstd, __ldg(g + col + 1), __ldg(b + col + 1));
+      __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
+      o[i] = *reinterpret_cast<uint32_t*>(&r);
+    }
+    *reinterpret_cast<uint4*>(u + (size_t)t * kD + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- weights --------------------------------------------------------------------------------------
+
+struct StateDict {
+  const char* const* names;
+  const float* const* data;
+  const int64_t* numel;
+  int n;
+  // find a tensor whose name ends with `suffix` (prefixes such as "net.backbone.backbone." are ignored)
+  int find(const std::string& suffix) const {
+    for (int i = 0; i < n; ++i) {
+      const size_t ln = strlen(names[i]);
+      if (ln >= suffix.size() && memcmp(names[i] + ln - suffix.size(), suffix.data(), suffix.size()) == 0) {
+        if (ln == suffix.size() || names[i][ln - suffix.size() - 1] == '.') return i;
+      }
+    }
+    return -1;
+  }
+};
+
+static int upload_f32(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd, const std::string& key, int64_t numel,
+                      float** out) {
+  const int i = sd.find(key);
+  if (i < 0) {
+    set_error("state dict has no tensor ending in '%s'", key.c_str());
+    return DCB200_EWEIGHT;
+  }
+  if (sd.numel[i] != numel) {
+    set_error("tensor '%s' has %lld elements, expected %lld", sd.names[i], (long long)sd.numel[i], (long long)numel);
+    return DCB200_EWEIGHT;
+  }
+  void* d = nullptr;
+  DCB_CUDA(cudaMalloc(&d, (size_t)numel * 4));
+  w->allocs.push_back(d);
+  DCB_CUDA(cudaMemcpyAsync(d, sd.data[i], (size_t)numel * 4, cudaMemcpyHostToDevice, ctx->stream));
+  *out = static_cast<float*>(d);
+  return DCB200_OK;
+}
+
+static int upload_bf16(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd, const std::string& key, int64_t numel,
+                       __nv_bfloat16** out) {
+  float* tmp = nullptr;
+  DCB_CHECK(upload_f32(ctx, w, sd, key, numel, &tmp));
+  void* d = nullptr;
+  DCB_CUDA(cudaMalloc(&d, (size_t)numel * 2));
+  w->allocs.push_back(d);
+  f32_to_bf16_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, ctx->stream>>>(tmp, static_cast<__nv_bfloat16*>(d), (size_t)numel);
+  DCB_LAUNCH_CHECK(ctx);
+  *out = static_cast<__nv_bfloat16*>(d);
+  return DCB200_OK;
+}
+
+int weights_destroy(dcb200_weights* w) {
+  if (!w) return DCB200_OK;
+  cudaSetDevice(w->device);
+  cudaDeviceSynchronize();
+  for (void* p : w->allocs) cudaFree(p);
+  delete w;
+  return DCB200_OK;
+}
+
+static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd) {
+  DCB_CHECK(upload_f32(ctx, w, sd, "embeddings.word_embeddings.weight", kVocab * kD, &w->emb));
+  // positional table length (= max_seq_len of the checkpoint)
+  const int iz = sd.find("layers.0.mixer.filter_fn.pos_emb.z");
+  if (iz < 0 || sd.numel[iz] % kEmbDim != 0) {
+    set_error("state dict has no usable 'layers.0.mixer.filter_fn.pos_emb.z'");
+    return DCB200_EWEIGHT;
+  }
+  w->Lmax = (int)(sd.numel[iz] / kEmbDim);
+  for (int l = 0; l < kLayers; ++l) {
+    LayerW& lw = w->layer[l];
+    const std::string p = "layers." + std::to_string(l) + ".";
+    DCB_CHECK(upload_bf16(ctx, w, sd, p + "mixer.in_linear.weight", 3 * kD * kD, &lw.w_in));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.in_linear.bias", 3 * kD, &lw.b_in));
+    DCB_CHECK(upload_bf16(ctx, w, sd, p + "mixer.out_linear.weight", kD * kD, &lw.w_out));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.out_linear.bias", kD, &lw.b_out));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.short_filter.weight", 3 * kD * 3, &lw.short_w));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.short_filter.bias", 3 * kD, &lw.short_b));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.filter_fn.bias", kD, &lw.filt_D));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm1.weight", kD, &lw.ln1_g));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm1.bias", kD, &lw.ln1_b));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm2.weight", kD, &lw.ln2_g));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm2.bias", kD, &lw.ln2_b));
+    DCB_CHECK(upload_bf16(ctx, w, sd, p + "mlp.fc1.weight", kInner * kD, &lw.w_fc1));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mlp.fc1.bias", kInner, &lw.b_fc1));
+    DCB_CHECK(upload_bf16(ctx, w, sd, p + "mlp.fc2.weight", kD * kInner, &lw.w_fc2));
+    DCB_CHECK(upload_f32(ctx, w, sd, p + "mlp.fc2.bias", kD, &lw.b_fc2));
+    // implicit filter, evaluated once for the whole positional table
+    FilterW fw;
+    float *z, *t, *w0, *b0, *f1, *w2, *b2, *f3, *w4, *b4, *f5, *w6, *dl;
+    const std::string f = p + "mixer.filter_fn.";
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "pos_emb.z", (int64_t)w->Lmax * kEmbDim, &z));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "pos_emb.t", w->Lmax, &t));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.0.weight", kFilterOrder * kEmbDim, &w0));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.0.bias", kFilterOrder, &b0));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.1.freq", kFilterOrder, &f1));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.2.weight", kFilterOrder * kFilterOrder, &w2));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.2.bias", kFilterOrder, &b2));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.3.freq", kFilterOrder, &f3));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.4.weight", kFilterOrder * kFilterOrder, &w4));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.4.bias", kFilterOrder, &b4));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.5.freq", kFilterOrder, &f5));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "implicit_filter.6.weight", kD * kFilterOrder, &w6));
+    DCB_CHECK(upload_f32(ctx, w, sd, f + "modulation.deltas", kD, &dl));
+    fw.z = z; fw.t = t; fw.w0 = w0; fw.b0 = b0; fw.f1 = f1; fw.w2 = w2; fw.b2 = b2; fw.f3 = f3;
+    fw.w4 = w4; fw.b4 = b4; fw.f5 = f5; fw.w6 = w6; fw.deltas = dl;
+    void* kbuf = nullptr;
+    DCB_CUDA(cudaMalloc(&kbuf, (size_t)kD * w->Lmax * 4));
+    w->allocs.push_back(kbuf);
+    lw.k = static_cast<float*>(kbuf);
+    implicit_filter_kernel<<<(w->Lmax + 127) / 128, 128, 0, ctx->stream>>>(fw, w->Lmax, lw.k);
+    DCB_LAUNCH_CHECK(ctx);
+    DCB_CHECK(make_tmap_2d(&lw.tm_in, lw.w_in, 3 * kD, kD, 128));
+    DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
+    DCB_CHECK(make_tmap_2d(&lw.tm_fc1, lw.w_fc1, kInner, kD, 256));
+    DCB_CHECK(make_tmap_2d(&lw.tm_fc2, lw.w_fc2, kD, kInner, 256));
+  }
+  DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.weight", kD, &w->lnf_g));
+  DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.bias", kD, &w->lnf_b));
+  DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear1.weight", kInner * kD, &w->wh1));
+  DCB_CHECK(upload_f32(ctx, w, sd, "head.linear1.bias", kInner, &w->bh1));
+  DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear2.weight", kInner * kInner, &w->wh2));
+  DCB_CHECK(upload_f32(ctx, w, sd, "head.linear2.bias", kInner, &w->bh2));
+  DCB_CHECK(upload_f32(ctx, w, sd, "head.linear3.weight", 2 * kInner, &w->w3));
+  DCB_CHECK(upload_f32(ctx, w, sd, "head.linear3.bias", 2, &w->b3));
+  DCB_CHECK(make_tmap_2d(&w->tm_h1, w->wh1, kInner, kD, 256));
+  DCB_CHECK(make_tmap_2d(&w->tm_h2, w->wh2, kInner, kInner, 256));
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging buffers of the caller may now be released
+  return DCB200_OK;
+}
+
+int weights_create(dcb200_ctx* ctx, const char* const* names, const float* const* data, const int64_t* numel,
+                   int32_t n, dcb200_weights** out) {
+  *out = nullptr;
+  dcb200_weights* w = new dcb200_weights();
+  w->device = ctx->device;
+  StateDict sd{names, data, numel, n};
+  const int rc = weights_fill(ctx, w, sd);
+  if (rc != DCB200_OK) {
+    weights_destroy(w);
+    return rc;
+  }
+  *out = w;
+  return DCB200_OK;
+}
+
+// twiddle table + per-layer filter spectra for FFT size N (built on first use, then cached)
+static int ensure_fft_size(dcb200_ctx* ctx, dcb200_weights* w, int N) {
+  if (w->tw.count(N)) return DCB200_OK;
+  void* t = nullptr;
+  DCB_CUDA(cudaMalloc(&t, (size_t)N * 8));
+  w->allocs.push_back(t);
+  twiddle_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(static_cast<float2*>(t), N);
+  DCB_LAUNCH_CHECK(ctx);
+  const FftPlan plan = make_plan(N);
+  for (int l = 0; l < kLayers; ++l) {
+    void* kf = nullptr;
+    DCB_CUDA(cudaMalloc(&kf, (size_t)kD * N * 8));
+    w->allocs.push_back(kf);
+    DCB_CHECK(launch_filter_spectrum(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, plan,
+                                     static_cast<float2*>(t), static_cast<float2*>(kf)));
+    w->layer[l].KF[N] = static_cast<float2*>(kf);
+  }
+  w->tw[N] = static_cast<float2*>(t);
+  return DCB200_OK;
+}
+
+int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
+                   float* logits, uint8_t* labels, int stop_stage) {
+  int stage = 0;
+#define DCB_STAGE_DONE()               \
+  do {                                 \
+    if (stage++ >= stop_stage) return DCB200_OK; \
+  } while (0)
+  dcb200_weights* w = const_cast<dcb200_weights*>(wc);  // lazily cached spectra
+  if (w->device != ctx->device) {
+    set_error("weights live on device %d, ctx on %d", w->device, ctx->device);
+    return DCB200_EINVAL;
+  }
+  int N = 256;
+  while (N < 2 * L) N <<= 1;
+  if (conv_smem_bytes(N, L) > 227 * 1024) {
+    set_error("L=%d: long-read (> 8192 tokens) convolution path is not built yet", L);
+    return DCB200_EINVAL;
+  }
+  DCB_CHECK(ensure_fft_size(ctx, w, N));
+  const size_t T = (size_t)B * L;
+  DevBuf& bhA = ctx->buf("act_hA");
+  DevBuf& bhB = ctx->buf("act_hB");
+  DevBuf& bu = ctx->buf("act_u");
+  DevBuf& bz = ctx->buf("act_z");
+  DevBuf& by = ctx->buf("act_y");
+  DevBuf& bg = ctx->buf("act_g");
+  DCB_CHECK(bhA.reserve(T * kD * 4));
+  DCB_CHECK(bhB.reserve(T * kD * 4));
+  DCB_CHECK(bu.reserve(T * kD * 2));
+  DCB_CHECK(bz.reserve(T * 3 * kD * 2));
+  DCB_CHECK(by.reserve(T * kD * 2));
+  DCB_CHECK(bg.reserve(T * kInner * 2));
+  float* hA = bhA.as<float>();
+  float* hB = bhB.as<float>();
+  __nv_bfloat16* u = bu.as<__nv_bfloat16>();
+  __nv_bfloat16* z = bz.as<__nv_bfloat16>();
+  __nv_bfloat16* y = by.as<__nv_bfloat16>();
+  __nv_bfloat16* g = bg.as<__nv_bfloat16>();
+
+  CUtensorMap tm_u, tm_y, tm_g;
+  DCB_CHECK(make_tmap_2d(&tm_u, u, T, kD, 128));
+  DCB_CHECK(make_tmap_3d_cm(&tm_y, y, B, kD, L));
+  DCB_CHECK(make_tmap_2d(&tm_g, g, T, kInner, 128));
+
+  {
+    int blocks = (int)((T + 7) / 8);
+    const int cap = ctx->sm_count * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    embed_ln_kernel<<<blocks, 256, 0, ctx->stream>>>(tok, w->emb, w->layer[0].ln1_g, w->layer[0].ln1_b, (int)T, hA, u);
+    DCB_LAUNCH_CHECK(ctx);
+  }
+  DCB_STAGE_DONE();
+  GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.T = (int)T;
+  gp.L = L;
+  gp.num_outer = (int)(T / 128);
+  const FftPlan plan = make_plan(N);
+  for (int l = 0; l < kLayers; ++l) {
+    LayerW& lw = w->layer[l];
+    GemmParams p = gp;
+    p.bias = lw.b_in;
+    p.out_bf16 = z;
+    DCB_CHECK(launch_gemm(ctx, G_INPROJ, lw.tm_in, tm_u, p));
+    DCB_STAGE_DONE();
+
+    ConvParams cp;
+    cp.z = z;
+    cp.y = y;
+    cp.short_w = lw.short_w;
+    cp.short_b = lw.short_b;
+    cp.KF = lw.KF[N];
+    cp.tw = w->tw[N];
+    cp.B = B;
+    cp.L = L;
+    cp.plan = plan;
+    DCB_CHECK(launch_fftconv(ctx, cp));
+    DCB_STAGE_DONE();
+
+    p = gp;
+    p.bias = lw.b_out;
+    p.resid = hA;
+    p.h_out = hB;
+    p.ln_g = lw.ln2_g;
+    p.ln_b = lw.ln2_b;
+    p.out_bf16 = u;
+    DCB_CHECK(launch_gemm(ctx, G_OUTPROJ, tm_y, lw.tm_out, p));
+    DCB_STAGE_DONE();
+
+    p = gp;
+    p.bias = lw.b_fc1;
+    p.out_bf16 = g;
+    DCB_CHECK(launch_gemm(ctx, G_FC1, tm_u, lw.tm_fc1, p));
+    DCB_STAGE_DONE();
+
+    p = gp;
+    p.bias = lw.b_fc2;
+    p.resid = hB;
+    p.h_out = (l + 1 < kLayers) ? hA : nullptr;
+    p.ln_g = (l + 1 < kLayers) ? w->layer[l + 1].ln1_g : w->lnf_g;
+    p.ln_b = (l + 1 < kLayers) ? w->layer[l + 1].ln1_b : w->lnf_b;
+    p.out_bf16 = u;
+    DCB_CHECK(launch_gemm(ctx, G_FC2, tm_g, lw.tm_fc2, p));
+    DCB_STAGE_DONE();
+  }
+  GemmParams p = gp;
+  p.bias = w->bh1;
+  p.qual = qual;
+  p.out_bf16 = g;
+  DCB_CHECK(launch_gemm(ctx, G_HEAD1, tm_u, w->tm_h1, p));
+  DCB_STAGE_DONE();
+  p = gp;
+  p.bias = w->bh2;
+  p.r_in = g;
+  p.w3 = w->w3;
+  p.b3 = w->b3;
+  p.logits = logits;
+  p.labels = labels;
+  DCB_CHECK(launch_gemm(ctx, G_HEAD2, tm_g, w->tm_h2, p));
+  return DCB200_OK;
+}
+
+}  // namespace dcb

@@ -92,10 +92,14 @@ int64_t dcb200_ctx_launch_count(dcb200_ctx* ctx);
 /* ---- FASTQ -> tokens + L2-normalised quality --------------------------------------------------
  * bytes: device-accessible FASTQ text (or any byte buffer holding seq and quality strings);
  * seq_off/qual_off[R]: byte offsets of each read's sequence / quality string, len[R]: bases kept
- * (already truncated to max_tokens-1 by the caller, tokenizer.py:154-163); Lpad >= max(len)+1.
- * Row r of tok/qual is LEFT padded: [PAD(4)...][bases][SEP(1)], qual 0 at pads and SEP. */
+ * (already truncated to max_tokens-1 by the caller, tokenizer.py:154-163); Lpad >= max(len)+1 is the
+ * collated batch length (the reference pads to the batch maximum); Lrow >= Lpad, Lrow % 4 == 0, is the
+ * row stride of tok/qual.  Row r = [PAD(4) x (Lpad-len-1)][bases][SEP(1)][PAD x (Lrow-Lpad)], qual 0
+ * at pads and SEP.  The left pads are what the reference feeds the model; the right filler only
+ * rounds the row up to the kernels' tile size -- the model is causal, so it cannot influence
+ * columns < Lpad. */
 int dcb200_encode_batch(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
-                        const int32_t* len, int32_t R, int32_t Lpad, uint8_t* tok, float* qual);
+                        const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual);
 
 /* ---- weights ------------------------------------------------------------------------------------
  * State dict as parallel arrays of names / host fp32 pointers / element counts.  Names are the
@@ -143,13 +147,24 @@ int dcb200_majority_voting_host(dcb200_ctx* ctx, const int8_t* labels, int64_t l
 
 /* ---- whole hot loop on host buffers ----------------------------------------------------------------
  * One batch of R reads out of a (pinned) host FASTQ buffer: H2D -> encode -> forward -> smooth/chop
- * -> D2H, synchronised on return.  logits_out [R,Lpad,2] / labels_out [R,Lpad] (host) may be NULL;
+ * -> D2H, synchronised on return.  Lpad is the collated batch length (any value >= max(len)+1; rows
+ * are rounded up to a multiple of 128 internally).  logits_out [R,Lpad,2] / labels_out [R,Lpad] (host) may be NULL;
  * interval outputs (host) as in dcb200_smooth_chop.  qual_lens may be NULL. */
 int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
                               const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
                               const int32_t* qual_lens, int32_t R, int32_t Lpad, const dcb200_chop_params* p,
                               float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
                               int32_t* n_keep, int32_t* keep_iv, uint8_t* action);
+
+/* ---- diagnostics (used by the parity tests to localise a mismatch) ---------------------------------
+ * dcb200_forward_debug == dcb200_forward that stops after `stop_stage` kernels of the forward chain
+ * (0 embed+LN1, then per layer l: 1+5l in_proj, 2+5l conv, 3+5l out_proj, 4+5l fc1, 5+5l fc2; 21 head1,
+ * 22 head2 = full).  dcb200_ctx_read_workspace copies a named internal activation buffer to the host:
+ * "act_hA"/"act_hB" fp32 [T,256] residual stream, "act_u" bf16 [T,256], "act_z" bf16 [B,768,L],
+ * "act_y" bf16 [B,256,L], "act_g" bf16 [T,1024].  Synchronises the stream. */
+int dcb200_forward_debug(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B,
+                         int32_t L, float* logits, uint8_t* labels, int32_t stop_stage);
+int dcb200_ctx_read_workspace(dcb200_ctx* ctx, const char* name, void* host_dst, int64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,163 @@
+"""-m gpu parity of the model path (dcb200_forward) against the fp32 oracle (oracle/hyena_ref.py),
+stage by stage for layer 0 and end to end on identical random-init weights and identical padded batches."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hyena_ref as H
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances (north star: "logits within a stated bf16/fp32 tolerance; labels bit-exact except at
+# stated near-tie positions"):
+LOGIT_ATOL_VS_FP32 = 5e-2     # |logit_gpu - logit_fp32_oracle|, bf16 operands / fp32 accumulate through 4 layers + head
+LOGIT_ATOL_VS_BF16EMU = 2e-2  # vs the oracle with bf16 rounding emulated at the same points
+NEAR_TIE = 1e-1               # positions with |l1 - l0| < NEAR_TIE in the fp32 oracle may flip
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return H.make_reference_model(0)
+
+
+@pytest.fixture(scope="module")
+def gpu(ref):
+    from deepchopper_b200.model import DeepChopper
+    return DeepChopper.from_state_dict(ref.state_dict(), device=0)
+
+
+def make_batch(rng, B, L, min_len=20):
+    ids = torch.full((B, L), 4, dtype=torch.int64)
+    q = torch.zeros((B, L), dtype=torch.float32)
+    for b in range(B):
+        n = int(rng.integers(min_len, L)) if b else L - 1
+        ids[b, L - 1 - n:L - 1] = torch.from_numpy(rng.integers(7, 11, n))
+        ids[b, L - 1] = 1
+        qq = torch.from_numpy(rng.integers(1, 50, n).astype(np.float32))
+        q[b, L - 1 - n:L - 1] = qq
+        q[b] = F.normalize(q[b], dim=0)
+    return ids, q
+
+
+def read_ws(model, name, shape, dtype):
+    from deepchopper_b200._native import check, lib
+    n = int(np.prod(shape))
+    if dtype == "bf16":
+        buf = torch.empty(n, dtype=torch.int16)
+        check(lib().dcb200_ctx_read_workspace(model._ctx_now().handle, name.encode(), C.c_void_p(buf.data_ptr()), n * 2))
+        return buf.view(torch.bfloat16).float().reshape(shape)
+    buf = torch.empty(n, dtype=torch.float32)
+    check(lib().dcb200_ctx_read_workspace(model._ctx_now().handle, name.encode(), C.c_void_p(buf.data_ptr()), n * 4))
+    return buf.reshape(shape)
+
+
+def run_debug(model, tok, q, stage):
+    from deepchopper_b200._native import check, lib
+    B, L = tok.shape
+    logits = torch.empty((B, L, 2), dtype=torch.float32, device="cuda")
+    labels = torch.empty((B, L), dtype=torch.uint8, device="cuda")
+    check(lib().dcb200_forward_debug(model._ctx_now().handle, model._weights.handle, C.c_void_p(tok.data_ptr()),
+                                     C.c_void_p(q.data_ptr()), B, L, C.c_void_p(logits.data_ptr()),
+                                     C.c_void_p(labels.data_ptr()), stage))
+    return logits, labels
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def close(name, got, want, atol, rtol):
+    err = (got - want).abs()
+    lim = atol + rtol * want.abs()
+    worst = (err - lim).max().item()
+    print(f"{name}: max|err|={err.max().item():.4g} mean|err|={err.mean().item():.4g} ref|mean|={want.abs().mean().item():.4g}")
+    assert worst <= 0, f"{name}: max err {err.max().item()} (|ref| mean {want.abs().mean().item()})"
+
+
+@pytest.mark.parametrize("B,L", [(4, 256), (3, 384)])
+def test_layer0_stage_by_stage(ref, gpu, B, L):
+    rng = np.random.default_rng(100 + B)
+    ids, q = make_batch(rng, B, L)
+    tok = ids.to(torch.uint8).cuda()
+    qd = q.cuda()
+    T = B * L
+    bb = ref.net.backbone.backbone
+    lay = bb.layers[0]
+    with torch.no_grad():
+        # stage 0: embedding + LN1
+        run_debug(gpu, tok, qd, 0)
+        hA = read_ws(gpu, "act_hA", (B, L, 256), "f32")
+        u = read_ws(gpu, "act_u", (B, L, 256), "bf16")
+        emb = bb.embeddings(ids)
+        assert torch.equal(hA, emb)
+        close("ln1", u, lay.norm1(emb), 1e-2, 1e-2)
+        # stage 1: in_proj (oracle op applied to the GPU's own bf16 input isolates the kernel)
+        run_debug(gpu, tok, qd, 1)
+        z = read_ws(gpu, "act_z", (B, 768, L), "bf16")
+        z_ref = F.linear(u, bf(lay.mixer.in_linear.weight), lay.mixer.in_linear.bias).transpose(1, 2)
+        close("in_proj", z, z_ref, 2e-2, 1e-2)
+        # stage 2: short conv + gate + long conv + gate
+        run_debug(gpu, tok, qd, 2)
+        y = read_ws(gpu, "act_y", (B, 256, L), "bf16")
+        zc = lay.mixer.short_filter(z)[..., :L]
+        x0, x1, v = zc.split(256, dim=1)
+        k = lay.mixer.filter_fn.filter(L)[0].transpose(0, 1)
+        y_ref = H.fftconv_ref(v * x1, k, lay.mixer.filter_fn.bias) * x0
+        close("hyena_conv", y, y_ref, 2e-2 * y_ref.abs().mean().item() + 1e-3, 1.5e-2)
+        # stage 3: out_proj + residual + LN2
+        run_debug(gpu, tok, qd, 3)
+        hB = read_ws(gpu, "act_hB", (B, L, 256), "f32")
+        m = read_ws(gpu, "act_u", (B, L, 256), "bf16")
+        h1_ref = F.linear(y.transpose(1, 2), bf(lay.mixer.out_linear.weight), lay.mixer.out_linear.bias) + hA
+        close("out_proj+res", hB, h1_ref, 1e-3 + 2e-3 * h1_ref.abs().mean().item(), 1e-3)
+        close("ln2", m, lay.norm2(hB), 1e-2, 1e-2)
+        # stage 4: fc1 + gelu
+        run_debug(gpu, tok, qd, 4)
+        g = read_ws(gpu, "act_g", (B, L, 1024), "bf16")
+        g_ref = F.gelu(F.linear(m, bf(lay.mlp.fc1.weight), lay.mlp.fc1.bias), approximate="tanh")
+        close("fc1+gelu", g, g_ref, 5e-3, 1e-2)
+        # stage 5: fc2 + residual + next LN1
+        run_debug(gpu, tok, qd, 5)
+        hA2 = read_ws(gpu, "act_hA", (B, L, 256), "f32")
+        u2 = read_ws(gpu, "act_u", (B, L, 256), "bf16")
+        h2_ref = F.linear(g, bf(lay.mlp.fc2.weight), lay.mlp.fc2.bias) + hB
+        close("fc2+res", hA2, h2_ref, 1e-3 + 2e-3 * h2_ref.abs().mean().item(), 1e-3)
+        close("ln1_next", u2, bb.layers[1].norm1(hA2), 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("B,L", [(4, 256), (5, 1024), (2, 2048), (16, 640)])
+def test_forward_logits_and_labels(ref, gpu, B, L):
+    rng = np.random.default_rng(7 * B + L)
+    ids, q = make_batch(rng, B, L)
+    with torch.no_grad():
+        want = ref(ids, q)
+        want_emu = ref(ids, q, emulate_bf16=True)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    close("logits vs fp32 oracle", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    close("logits vs bf16-emulating oracle", got, want_emu, LOGIT_ATOL_VS_BF16EMU, 0.0)
+    lab_got = got[..., 1] > got[..., 0]
+    lab_want = want[..., 1] > want[..., 0]
+    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
+    print(f"decided fraction {decided.float().mean().item():.4f}, flips overall {(lab_got != lab_want).float().mean().item():.5f}")
+    assert decided.float().mean() > 0.5
+    assert torch.equal(lab_got[decided], lab_want[decided])
+    # the u8 label output is exactly `logit1 > logit0` of the logits the same call returns
+    tok = ids.to(torch.uint8).cuda()
+    lg, lb = gpu.forward_tokens(tok, q.cuda(), True, True)
+    assert torch.equal(lb.bool(), lg[..., 1] > lg[..., 0])
+
+
+def test_forward_arbitrary_length_is_right_filled(ref, gpu):
+    # reference API accepts any [B, L]; rows are right-filled to the 128-token tile (causal => inert)
+    rng = np.random.default_rng(9)
+    ids, q = make_batch(rng, 3, 333)
+    with torch.no_grad():
+        want = ref(ids, q)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    assert got.shape == (3, 333, 2)
+    close("logits L=333", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    lg, lab = gpu.predict_step({"input_ids": ids, "input_quals": q, "labels": torch.zeros(3, 333, dtype=torch.int8)})
+    assert lg.shape == (3, 333, 2) and lab.shape == (3, 333)
