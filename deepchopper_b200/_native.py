@@ -13,7 +13,8 @@ EXPORTS = [
     "dcb200_ctx_sync", "dcb200_ctx_stream", "dcb200_ctx_launch_count", "dcb200_encode_batch", "dcb200_weights_create",
     "dcb200_weights_destroy", "dcb200_forward", "dcb200_smooth_chop", "dcb200_smooth_chop_logits",
     "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
-    "dcb200_forward_debug", "dcb200_ctx_read_workspace",
+    "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
+    "dcb200_kernel_kind_name",
 ]
 
 
@@ -65,6 +66,10 @@ def lib():
     l.dcb200_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     l.dcb200_forward_debug.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i32]
     l.dcb200_ctx_read_workspace.argtypes = [vp, C.c_char_p, vp, i64]
+    l.dcb200_ctx_profile.argtypes = [vp, C.c_int]
+    l.dcb200_ctx_profile_read.argtypes = [vp, vp, vp, i32, i32]
+    l.dcb200_kernel_kind_name.argtypes = [i32]
+    l.dcb200_kernel_kind_name.restype = C.c_char_p
     pp = C.POINTER(ChopParams)
     l.dcb200_smooth_chop.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_smooth_chop_logits.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
@@ -73,7 +78,8 @@ def lib():
     l.dcb200_majority_voting_host.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]
     l.dcb200_predict_batch_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, pp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("dcb200_last_error", "dcb200_chop_params_default", "dcb200_ctx_stream", "dcb200_ctx_launch_count"):
+        if name not in ("dcb200_last_error", "dcb200_chop_params_default", "dcb200_ctx_stream", "dcb200_ctx_launch_count",
+                        "dcb200_kernel_kind_name"):
             getattr(l, name).restype = C.c_int
     _lib = l
     return l
@@ -108,6 +114,22 @@ class Context:
     @property
     def launches(self) -> int:
         return int(lib().dcb200_ctx_launch_count(self._h))
+
+    def profile(self, enable: bool = True):
+        check(lib().dcb200_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kernel kind: (total ms, launches)} measured with CUDA events on this ctx's stream."""
+        n = 16
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        check(lib().dcb200_ctx_profile_read(self._h, ms, cnt, n, 1 if reset else 0))
+        out = {}
+        for i in range(n):
+            name = lib().dcb200_kernel_kind_name(i)
+            if name and cnt[i]:
+                out[name.decode()] = (float(ms[i]), int(cnt[i]))
+        return out
 
     def close(self):
         if self._h:

@@ -99,6 +99,11 @@ int dcb200_ctx_destroy(dcb200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->ws) kv.second.release();
+  for (auto& r : ctx->prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return DCB200_OK;
@@ -147,6 +152,52 @@ int dcb200_forward_debug(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t
   DCB_CHECK(forward_device(ctx, w, tok, qual, B, L, logits, labels, stop_stage));
   DCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return DCB200_OK;
+}
+
+static int prof_collect(dcb200_ctx* ctx) {
+  if (ctx->prof_recs.empty()) return DCB200_OK;
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ctx->prof_ms[r.kind] += ms;
+      ctx->prof_cnt[r.kind] += 1;
+    }
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_recs.clear();
+  return DCB200_OK;
+}
+
+int dcb200_ctx_profile(dcb200_ctx* ctx, int enable) {
+  DCB_ARG(ctx != nullptr);
+  DCB_CUDA(cudaSetDevice(ctx->device));
+  DCB_CHECK(prof_collect(ctx));
+  ctx->profiling = enable != 0;
+  return DCB200_OK;
+}
+
+int dcb200_ctx_profile_read(dcb200_ctx* ctx, double* ms, int64_t* counts, int32_t n, int32_t reset) {
+  DCB_ARG(ctx && ms && counts && n >= 0);
+  DCB_CUDA(cudaSetDevice(ctx->device));
+  DCB_CHECK(prof_collect(ctx));
+  for (int i = 0; i < n; ++i) {
+    ms[i] = i < K_NKINDS ? ctx->prof_ms[i] : 0.0;
+    counts[i] = i < K_NKINDS ? ctx->prof_cnt[i] : 0;
+  }
+  if (reset)
+    for (int i = 0; i < K_NKINDS; ++i) {
+      ctx->prof_ms[i] = 0.0;
+      ctx->prof_cnt[i] = 0;
+    }
+  return DCB200_OK;
+}
+
+const char* dcb200_kernel_kind_name(int32_t kind) {
+  static const char* names[K_NKINDS] = {"encode", "embed_ln", "in_proj", "hyena_conv", "out_proj", "fc1", "fc2",
+                                        "head1", "head2", "smooth_chop", "other"};
+  return (kind >= 0 && kind < K_NKINDS) ? names[kind] : nullptr;
 }
 
 int dcb200_ctx_read_workspace(dcb200_ctx* ctx, const char* name, void* host_dst, int64_t bytes) {

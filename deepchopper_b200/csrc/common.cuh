@@ -66,6 +66,14 @@ struct DevBuf {
 
 }  // namespace dcb
 
+namespace dcb {
+enum KernelKind { K_ENCODE = 0, K_EMBED, K_INPROJ, K_CONV, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_SMOOTH, K_OTHER, K_NKINDS };
+struct ProfRec {
+  int kind;
+  cudaEvent_t a, b;
+};
+}  // namespace dcb
+
 struct dcb200_ctx {
   int device = 0;
   int sm_count = 148;
@@ -75,7 +83,46 @@ struct dcb200_ctx {
   // named workspaces (activations, staging), grow-only
   std::map<std::string, dcb::DevBuf> ws;
   dcb::DevBuf& buf(const char* name) { return ws[name]; }
+  // optional per-kernel CUDA-event timing (bench.py's roofline numbers)
+  bool profiling = false;
+  std::vector<dcb::ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[dcb::K_NKINDS] = {0};
+  int64_t prof_cnt[dcb::K_NKINDS] = {0};
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) {
+      cudaEvent_t e = prof_pool.back();
+      prof_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
 };
+
+namespace dcb {
+// Brackets the kernel launches of one scope with events on the ctx stream when profiling is on.
+struct ProfScope {
+  dcb200_ctx* ctx;
+  ProfRec rec;
+  bool on;
+  ProfScope(dcb200_ctx* c, int kind) : ctx(c), on(c->profiling) {
+    if (on) {
+      rec.kind = kind;
+      rec.a = ctx->prof_event();
+      rec.b = ctx->prof_event();
+      cudaEventRecord(rec.a, ctx->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(rec.b, ctx->stream);
+      ctx->prof_recs.push_back(rec);
+    }
+  }
+};
+}  // namespace dcb
 
 #define DCB_LAUNCH_CHECK(ctx)                                                              \
   do {                                                                                     \

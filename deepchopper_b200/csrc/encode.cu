@@ -83,6 +83,7 @@ int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off,
   int blocks = (R + 7) / 8;
   const int cap = ctx->sm_count * 8 * 4;
   if (blocks > cap) blocks = cap;
+  ProfScope prof(ctx, K_ENCODE);
   encode_kernel<<<blocks, threads, 0, ctx->stream>>>(bytes, seq_off, qual_off, len, R, Lpad, Lrow, tok, qual);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;

@@ -306,6 +306,7 @@ int launch_fftconv(dcb200_ctx* ctx, const ConvParams& p) {
     configured = 227 * 1024;
   }
   dim3 grid((p.B + 1) / 2, 256);
+  ProfScope prof(ctx, K_CONV);
   fftconv_kernel<<<grid, conv_threads(p.plan.N), smem, ctx->stream>>>(p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;

@@ -353,6 +353,8 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
     configured = true;
   }
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
+  static const int kinds[6] = {K_INPROJ, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2};
+  ProfScope prof(ctx, kinds[MODE]);
   gemm_kernel<MODE><<<grid, 256, smem, ctx->stream>>>(a, b, p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;

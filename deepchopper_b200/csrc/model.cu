@@ -358,6 +358,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     int blocks = (int)((T + 7) / 8);
     const int cap = ctx->sm_count * 8 * 4;
     if (blocks > cap) blocks = cap;
+    ProfScope prof(ctx, K_EMBED);
     embed_ln_kernel<<<blocks, 256, 0, ctx->stream>>>(tok, w->emb, w->layer[0].ln1_g, w->layer[0].ln1_b, (int)T, hA, u);
     DCB_LAUNCH_CHECK(ctx);
   }

@@ -419,6 +419,7 @@ static int launch_smooth(dcb200_ctx* ctx, SmoothArgs a) {
   const int64_t cap = (int64_t)ctx->sm_count * 8 * 4;  // 8 resident 256-thread CTAs per SM, a few waves; grid-stride beyond
   int blocks = (int)(blocks64 < cap ? blocks64 : cap);
   const bool logits = a.logits != nullptr;
+  ProfScope prof(ctx, K_SMOOTH);
   if (window > 63) {
     // rare parameterisation: recount literally, then run the interval pass with window 1
     dcb::DevBuf& scratch = ctx->buf("smooth_scratch");

@@ -166,6 +166,14 @@ int dcb200_forward_debug(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t
                          int32_t L, float* logits, uint8_t* labels, int32_t stop_stage);
 int dcb200_ctx_read_workspace(dcb200_ctx* ctx, const char* name, void* host_dst, int64_t bytes);
 
+/* Per-kernel device timing with CUDA events on the ctx stream (bench.py's roofline figures).
+ * dcb200_ctx_profile(ctx, 1) starts bracketing every kernel launch with an event pair;
+ * dcb200_ctx_profile_read sums elapsed milliseconds and launch counts per kernel kind
+ * (index -> dcb200_kernel_kind_name) into ms[n] / counts[n], optionally resetting the sums. */
+int dcb200_ctx_profile(dcb200_ctx* ctx, int enable);
+int dcb200_ctx_profile_read(dcb200_ctx* ctx, double* ms, int64_t* counts, int32_t n, int32_t reset);
+const char* dcb200_kernel_kind_name(int32_t kind);
+
 #ifdef __cplusplus
 }
 #endif
