@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
           const int ct = a.p.chop_type;
           if ((ct == DCB200_CHOP_TERMINAL && !terminal) || (ct == DCB200_CHOP_INTERNAL && terminal) ||
               (nk > 0 && first_len == (int)n)) {
-            nk = 0;  // passthrough, src/output/split.rs:191-201
+            nk = 0;  // rebuilt, uncut record: src/output/split.rs:191-201
+            act = DCB200_ACTION_UNCHOPPED;
           } else {
             act = terminal ? DCB200_ACTION_CHOP_T : DCB200_ACTION_CHOP_I;
           }

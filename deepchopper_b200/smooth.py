@@ -15,7 +15,7 @@ import numpy as np
 from . import _native
 from ._native import ChopParams, Context, check, default_context, lib
 
-ACTION_PASSTHROUGH, ACTION_CHOP_T, ACTION_CHOP_I, ACTION_ADAPTERS = 0, 1, 2, 3
+ACTION_PASSTHROUGH, ACTION_CHOP_T, ACTION_CHOP_I, ACTION_ADAPTERS, ACTION_UNCHOPPED = 0, 1, 2, 3, 4
 CHOP_TYPES = {"terminal": 0, "internal": 1, "all": 2}
 
 # src/default.rs

@@ -46,6 +46,8 @@ extern "C" {
 #define DCB200_ACTION_CHOP_T 1      /* emit keep_iv pieces named "{id}|s:e|T" */
 #define DCB200_ACTION_CHOP_I 2      /* emit keep_iv pieces named "{id}|s:e|I" */
 #define DCB200_ACTION_ADAPTERS 3    /* --ocq: emit adapter_iv pieces named "{id}|s:e" */
+#define DCB200_ACTION_UNCHOPPED 4   /* chop-type mismatch (src/output/split.rs:191-201): emit "@{id}" (no description)
+                                       with the prediction-decoded sequence and the FASTQ quality, uncut */
 
 #define DCB200_CHOP_TERMINAL 0
 #define DCB200_CHOP_INTERNAL 1

@@ -21,6 +21,7 @@
 #define DCREF_ACTION_CHOP_T 1
 #define DCREF_ACTION_CHOP_I 2
 #define DCREF_ACTION_ADAPTERS 3
+#define DCREF_ACTION_UNCHOPPED 4
 #define DCREF_CHOP_TERMINAL 0
 #define DCREF_CHOP_INTERNAL 1
 #define DCREF_CHOP_ALL 2
@@ -112,6 +113,7 @@ static void dcref_one(const int8_t* labels, int64_t n, int64_t qual_len, int win
   int terminal = before == 1;                                   /* split.rs:185-189 */
   if ((chop_type == DCREF_CHOP_TERMINAL && !terminal) || (chop_type == DCREF_CHOP_INTERNAL && terminal) ||
       (nk > 0 && first_len == n)) {                             /* split.rs:191-201 */
+    *action = DCREF_ACTION_UNCHOPPED;
     return;
   }
   *n_keep = (int32_t)nk;

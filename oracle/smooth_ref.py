@@ -259,7 +259,7 @@ def chop_records(fastq: Sequence[FastqRecord], predicts: dict, opt: ChopOptions)
 
 # ---- chop coordinates in the flat form the C-ABI returns (same gating, numbers only) -------------
 
-ACTION_PASSTHROUGH, ACTION_CHOP_T, ACTION_CHOP_I, ACTION_ADAPTERS = 0, 1, 2, 3
+ACTION_PASSTHROUGH, ACTION_CHOP_T, ACTION_CHOP_I, ACTION_ADAPTERS, ACTION_UNCHOPPED = 0, 1, 2, 3, 4
 
 
 def chop_coordinates(labels: Sequence[int], qual_len: Optional[int], opt: ChopOptions):
@@ -267,7 +267,7 @@ def chop_coordinates(labels: Sequence[int], qual_len: Optional[int], opt: ChopOp
 
     ``labels`` is the per-base prediction of one read (len == decoded seq len);
     ``qual_len`` the FASTQ quality length (None == same as len(labels)).
-    action PASSTHROUGH -> emit the FASTQ record verbatim; CHOP_T/CHOP_I -> emit ``kept`` pieces
+    action PASSTHROUGH -> emit the FASTQ record verbatim; UNCHOPPED -> emit ``@{id}`` + decoded seq + qual, uncut; CHOP_T/CHOP_I -> emit ``kept`` pieces
     named ``{id}|s:e|T`` / ``|I``; ADAPTERS (--ocq) -> emit ``adapter`` pieces ``{id}|s:e``.
     """
     n = len(labels)
@@ -288,7 +288,7 @@ def chop_coordinates(labels: Sequence[int], qual_len: Optional[int], opt: ChopOp
     if ((opt.chop_type == CHOP_TERMINAL and current == CHOP_INTERNAL)
             or (opt.chop_type == CHOP_INTERNAL and current == CHOP_TERMINAL)
             or (len(kept) > 0 and kept[0][1] - kept[0][0] == n)):
-        return ACTION_PASSTHROUGH, ivs, []
+        return ACTION_UNCHOPPED, ivs, []
     return (ACTION_CHOP_T if current == CHOP_TERMINAL else ACTION_CHOP_I), ivs, kept
 
 

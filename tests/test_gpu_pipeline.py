@@ -1,0 +1,139 @@
+"""-m gpu end-to-end parity: prediction directory -> chop output (decompressed bytes identical to the
+oracle's restatement of deepchopper-chop), CLI predict -> .pt layout, host vs device pipelines."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deepchopper_b200 import synth
+from oracle import hyena_ref as H
+from oracle import smooth_ref as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _planted_batches(recs, rng, batch=16):
+    from deepchopper_b200 import encode, writer
+    buf = np.frombuffer(synth.fastq_text(recs), dtype=np.uint8)
+    ix = encode.index_fastq(buf)
+    lens_all = ix.seq_len.astype(np.int64)
+    lab, starts, _ = synth.planted_labels(rng, lens_all)
+    table = np.zeros(256, np.uint8)
+    for k, v in {ord("A"): 7, ord("C"): 8, ord("G"): 9, ord("T"): 10, ord("N"): 11}.items():
+        table[k] = v
+    dicts = []
+    for i in range(0, len(recs), batch):
+        rows = np.arange(i, min(len(recs), i + batch))
+        lens = lens_all[rows]
+        Lpad = int(lens.max()) + 1
+        tok = torch.full((rows.size, Lpad), 4, dtype=torch.uint8)
+        qual = torch.zeros((rows.size, Lpad))
+        logits = torch.zeros((rows.size, Lpad, 2))
+        for k, r in enumerate(rows):
+            n = int(lens[k])
+            tok[k, Lpad - 1 - n:Lpad - 1] = torch.from_numpy(table[np.frombuffer(ix.seq(r), dtype=np.uint8)])
+            tok[k, Lpad - 1] = 1
+            l = torch.from_numpy(lab[starts[r]:starts[r] + n].astype(np.float32))
+            m = torch.from_numpy(rng.random(n).astype(np.float32)) + 0.05
+            logits[k, Lpad - 1 - n:Lpad - 1, 1] = l * m
+            logits[k, Lpad - 1 - n:Lpad - 1, 0] = (1 - l) * m
+        logits[:, 0, :] = 0.3                                    # ties / junk at ignored positions must not matter
+        dicts.append(writer.batch_dict(logits, tok, qual, encode.id_rows(ix, rows, np.zeros(rows.size, bool)), lens, Lpad))
+    return dicts
+
+
+def _oracle_text(dicts, recs, opt):
+    preds = {}
+    for d in dicts:
+        preds.update(S.load_predicts_from_batch(d["prediction"].numpy(), d["target"].numpy(), d["seq"].numpy(), d["id"].numpy()))
+    fq = [S.FastqRecord(rid.split(" ")[0], rid.partition(" ")[2], s, q) for rid, s, q in recs]
+    out = S.chop_records(fq, preds, opt)
+    return "".join(r.to_text() for r in out), len(preds), len(out)
+
+
+@pytest.mark.parametrize("chop_type,ocq", [("all", False), ("terminal", False), ("internal", False), ("all", True)])
+def test_chop_output_bit_exact(tmp_path, chop_type, ocq):
+    from deepchopper_b200 import writer
+    from deepchopper_b200.chop import chop_fastq, params_from_cli
+    rng = np.random.default_rng(42)
+    lens = np.concatenate([synth.read_lengths(rng, 150, hi=3000), rng.integers(20, 150, 10)])
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    recs[3] = (recs[3][0] + " some description", recs[3][1], recs[3][2])     # description survives only on passthrough
+    dicts = _planted_batches(recs, rng)
+    # a FASTQ record without prediction is dropped; a truncated prediction passes through
+    fq_recs = list(recs) + [("nopred", "ACGT" * 50, "I" * 200)]
+    long_id = recs[7][0]
+    fq_recs[7] = (long_id, recs[7][1] + "ACGTACGT", recs[7][2] + "IIIIIIII")
+    fq_path = tmp_path / "reads.fq"
+    fq_path.write_bytes(synth.fastq_text(fq_recs))
+    pdir = tmp_path / "predictions"
+    for i, d in enumerate(dicts):
+        writer.write_batch(str(pdir), 0, i, d)
+    params = params_from_cli(chop_type=chop_type, output_chopped=ocq)
+    out, npred, nrec = chop_fastq([str(pdir / "0")], str(fq_path), params, output_prefix=str(tmp_path / "out"))
+    want, want_pred, want_rec = _oracle_text(dicts, fq_recs, S.ChopOptions(chop_type=chop_type, output_chopped_seqs=ocq))
+    assert os.path.basename(out) == f"out.{want_pred}pd.{want_rec}record.chop.fq.gz"   # src/bin/predict.rs:342-352
+    got = gzip.open(out, "rb").read().decode()
+    assert (npred, nrec) == (want_pred, want_rec)
+    assert got == want
+    if not ocq and chop_type == "all":
+        assert "|T\n" in got and "|I\n" in got                   # the planted set exercises both chop kinds
+
+
+def test_cli_predict_layout_and_logits(tmp_path):
+    from deepchopper_b200 import cli
+    from deepchopper_b200.init_weights import random_state_dict
+    rng = np.random.default_rng(5)
+    recs = synth.fastq_reads(rng, 30, 150, 900)
+    fq = tmp_path / "x.fastq"
+    fq.write_bytes(synth.fastq_text(recs))
+    out = tmp_path / "predictions"
+    cli.main(["predict", str(fq), "-o", str(out), "--random-init", "-b", "12", "--gpus", "1"])
+    files = sorted(os.listdir(out / "0"))
+    assert files == ["0_0.pt", "0_1.pt", "0_2.pt"]              # {global_rank}_{batch_idx}.pt, callbacks.py:25
+    ref = H.make_reference_model(0)
+    ref.load_state_dict(random_state_dict(0))
+    d = torch.load(out / "0" / "0_1.pt")
+    feats = [H.tokenize_read(*recs[i]) for i in range(12, 24)]
+    batch = H.collate(feats)
+    assert torch.equal(d["seq"], batch["input_ids"])
+    assert torch.equal(d["target"], batch["labels"].to(torch.int64))
+    assert torch.equal(d["id"], batch["id"].to(torch.int64))
+    np.testing.assert_allclose(d["qual"].numpy(), batch["input_quals"].numpy(), rtol=1e-6, atol=1e-9)
+    with torch.no_grad():
+        want = ref(batch["input_ids"], batch["input_quals"])
+    assert (d["prediction"] - want).abs().max() < 2e-2
+    # chop on those predictions == oracle chop on the same predictions
+    from deepchopper_b200.chop import chop_fastq
+    o, npred, nrec = chop_fastq([str(out / "0")], str(fq), output_prefix=str(tmp_path / "y"))
+    dicts = [torch.load(out / "0" / f) for f in files]
+    want_txt, wp, wr = _oracle_text(dicts, recs, S.ChopOptions())
+    assert gzip.open(o, "rb").read().decode() == want_txt and (npred, nrec) == (wp, wr)
+
+
+def test_host_pipeline_equals_device_pipeline():
+    from deepchopper_b200.init_weights import random_state_dict
+    from deepchopper_b200.model import DeepChopper
+    from deepchopper_b200.predict import DevicePipeline, HostPipeline, plan_batches
+    rng = np.random.default_rng(8)
+    lens = synth.read_lengths(rng, 300, hi=2500)
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    blob = np.frombuffer(("".join(r[1] for r in recs) + "".join(r[2] for r in recs)).encode(), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    model = DeepChopper.from_state_dict(random_state_dict(0), device=0)
+    batches = plan_batches(lens, token_budget=64 * 1024)
+    dp = DevicePipeline(model)
+    dp.upload(blob, off, off + int(lens.sum()), lens, batches)
+    hp = HostPipeline(model)
+    hp.pack(blob, off, off + int(lens.sum()), lens, batches)
+    for di, hi in zip(dp.items, hp.items):
+        b = di[0]
+        labels_h = np.zeros((b.rows.size, b.Lpad), np.uint8)
+        o = hp.run_batch(hi, labels_h)
+        _, labels_d, (n_ad, ad, n_keep, keep, act) = dp.run_batch(di)
+        torch.cuda.synchronize()
+        assert np.array_equal(labels_d.cpu().numpy()[:, :b.Lpad], labels_h)
+        assert np.array_equal(o["n_adapter"], n_ad.cpu().numpy()) and np.array_equal(o["action"], act.cpu().numpy())
+        assert np.array_equal(o["adapter_iv"], ad.cpu().numpy()) and np.array_equal(o["keep_iv"], keep.cpu().numpy())
