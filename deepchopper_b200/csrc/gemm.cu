@@ -1,10 +1,12 @@
 // Persistent, warp-specialised tcgen05 GEMMs with fused epilogues for the Hyena layers and the head.
 //
-//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a 4-stage smem ring
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a 3/4-stage smem ring
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128/256, K=16) into TMEM
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue: tcgen05.ld the fp32 accumulator (thread == one of the 128 rows) and apply the
-//               fused epilogue while the MMA warp fills the other TMEM accumulator stage
+//   warps 4-11  epilogue (two warps per TMEM lane quadrant, each owning half of the columns): tcgen05.ld
+//               the fp32 accumulator, transpose through a private smem stage so that every global load /
+//               store instruction covers whole 128-byte lines, apply the fused epilogue, while the MMA
+//               warp fills the other TMEM accumulator stage
 //
 // Modes (reference ops they replace, SURVEY Appendix A / K3,K6,K7,K8):
 //   INPROJ   z^T = W_in . LN1(h)^T + b      -> bf16 channel-major [B,768,L]  (operand roles swapped so
@@ -23,17 +25,21 @@ namespace dcb {
 
 using namespace ptx;
 
-constexpr int kStages = 4;
 constexpr int kTileM = 128;
-constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each owning half of the accumulator columns
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kStagePitch = 144;                    // bytes per staged row: 128 B payload + 16 B pad (conflict-free)
+constexpr int kStageBytes = 32 * kStagePitch;       // per epilogue warp
+constexpr int kVecFloats = 3 * 1024;                // column vectors cached in smem (bias / LN gamma,beta / linear3)
 
 template <int MODE> struct Traits;
-template <> struct Traits<G_INPROJ>  { static constexpr int K = 256,  NT = 128, INNER = 6; static constexpr bool A_MN = false; };
-template <> struct Traits<G_OUTPROJ> { static constexpr int K = 256,  NT = 256, INNER = 1; static constexpr bool A_MN = true;  };
-template <> struct Traits<G_FC1>     { static constexpr int K = 256,  NT = 256, INNER = 4; static constexpr bool A_MN = false; };
-template <> struct Traits<G_FC2>     { static constexpr int K = 1024, NT = 256, INNER = 1; static constexpr bool A_MN = false; };
-template <> struct Traits<G_HEAD1>   { static constexpr int K = 256,  NT = 256, INNER = 4; static constexpr bool A_MN = false; };
-template <> struct Traits<G_HEAD2>   { static constexpr int K = 1024, NT = 256, INNER = 4; static constexpr bool A_MN = false; };
+template <> struct Traits<G_INPROJ>  { static constexpr int K = 256,  NT = 128, INNER = 6, STAGES = 4; static constexpr bool A_MN = false; };
+template <> struct Traits<G_OUTPROJ> { static constexpr int K = 256,  NT = 256, INNER = 1, STAGES = 3; static constexpr bool A_MN = true;  };
+template <> struct Traits<G_FC1>     { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
+template <> struct Traits<G_FC2>     { static constexpr int K = 1024, NT = 256, INNER = 1, STAGES = 3; static constexpr bool A_MN = false; };
+template <> struct Traits<G_HEAD1>   { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
+template <> struct Traits<G_HEAD2>   { static constexpr int K = 1024, NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -41,26 +47,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   (F.gelu(approximate="tanh"))
-  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.0f + t);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Tr = Traits<MODE>;
   constexpr int NT = Tr::NT;
+  constexpr int kStages = Tr::STAGES;
   constexpr int KCH = Tr::K / kBlockK;
   constexpr uint32_t A_BYTES = kTileM * 128;
   constexpr uint32_t B_BYTES = NT * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * NT;
+  constexpr int HALF = NT / 2;  // accumulator columns owned by one epilogue warp
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+  uint8_t* stage_area = smem + kStages * STAGE_BYTES;                       // kEpiWarps * kStageBytes
+  float* vec = reinterpret_cast<float*>(stage_area + kEpiWarps * kStageBytes);  // kVecFloats
+  float2* stats = reinterpret_cast<float2*>(vec + kVecFloats);              // [2 parity][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * 2 * 128);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   const uint32_t smem_base = smem_u32(smem);
@@ -84,13 +99,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
     tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
     tmem_relinquish();
+  }
+  // column vectors -> smem (epilogue warps read them as broadcast / lane-fixed float4)
+  if (MODE == G_OUTPROJ || MODE == G_FC2) {
+    for (int i = threadIdx.x; i < 256; i += kThreads) {
+      vec[i] = p.bias[i];
+      vec[1024 + i] = p.ln_g[i];
+      vec[2048 + i] = p.ln_b[i];
+    }
+  } else if (MODE == G_FC1 || MODE == G_HEAD1) {
+    for (int i = threadIdx.x; i < 1024; i += kThreads) vec[i] = p.bias[i];
+  } else if (MODE == G_HEAD2) {
+    for (int i = threadIdx.x; i < 1024; i += kThreads) {
+      vec[i] = p.bias[i];
+      vec[1024 + i] = p.w3[i];
+      vec[2048 + i] = p.w3[1024 + i];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -174,152 +205,265 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int e = warp - 4;            // == warp % 4: the TMEM lane quadrant this warp may access
-    const int row_in_tile = e * 32 + lane;
+    // Row-owner layout (what tcgen05.ld 32x32b gives): thread == accumulator row `quad*32 + lane`.
+    // T layout (what global memory wants): lane -> (row 4i + lane/8, 16-byte piece lane%8) of a 128-byte
+    // wide row chunk, so one warp instruction touches 4 full 128-byte lines.  The per-warp smem stage
+    // converts between the two.
+    const int e = warp - 4;
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int half = e >> 2;     // which half of the accumulator columns
+    uint8_t* stg = stage_area + e * kStageBytes;
+    const uint32_t stg_own = smem_u32(stg) + lane * kStagePitch;                       // my row (row-owner)
+    const int trow0 = lane >> 3, piece = lane & 7;
+    const uint8_t* stg_t = stg + trow0 * kStagePitch + piece * 16;                     // + i * 4 * kStagePitch
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t tile_parity = 0;
     uint32_t v[32];
+    float4 rpre0[8], rpre1[8];  // LN modes: residual of the next two column chunks (T layout)
+    if ((MODE == G_OUTPROJ || MODE == G_FC2) && (int)blockIdx.x < num_outer) {
+      const size_t r0 = (size_t)blockIdx.x * kTileM + quad * 32 + trow0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rpre0[i] = *reinterpret_cast<const float4*>(p.resid + (r0 + 4 * i) * 256 + half * HALF + piece * 4);
+        rpre1[i] = *reinterpret_cast<const float4*>(p.resid + (r0 + 4 * i) * 256 + half * HALF + piece * 4 + 32);
+      }
+    }
     for (int o = blockIdx.x; o < num_outer; o += gridDim.x) {
       const int tok0 = o * kTileM;
-      float lg0 = 0.f, lg1 = 0.f;  // HEAD2 partial logits
-      for (int i = 0; i < Tr::INNER; ++i) {
+      float lg0[8], lg1[8];  // HEAD2 partial logits of my 8 T-layout rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lg0[i] = lg1[i] = 0.f;
+      for (int it = 0; it < Tr::INNER; ++it) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + acc * NT + ((uint32_t)(e * 32) << 16);
+        const uint32_t t_row = tmem_base + acc * NT + half * HALF + ((uint32_t)(quad * 32) << 16);
 
-        if (MODE == G_INPROJ) {
-          const int ch = i * kTileM + row_in_tile;
-          const float bias = __ldg(p.bias + ch);
-          const int b = tok0 / p.L, l0 = tok0 % p.L;
-          __nv_bfloat16* dst = p.out_bf16 + ((size_t)b * 768 + ch) * p.L + l0;
+        if (MODE == G_INPROJ || MODE == G_FC1 || MODE == G_HEAD1) {
+          // ---- bf16 output, element-wise epilogue: 64 columns (128 B of bf16) per staged group -------------
+          const size_t own_row = (size_t)tok0 + quad * 32 + lane;
+          float rowv = 0.f;  // INPROJ: bias of my channel row; HEAD1: quality of my token row
+          if (MODE == G_INPROJ) rowv = __ldg(p.bias + it * kTileM + quad * 32 + lane);
+          if (MODE == G_HEAD1) rowv = __ldg(p.qual + own_row);
 #pragma unroll 1
-          for (int c = 0; c < NT / 32; ++c) {
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
-            uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+          for (int grp = 0; grp < HALF / 64; ++grp) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(v[8 * q + 0]) + bias, __uint_as_float(v[8 * q + 1]) + bias);
-              w.y = pack_bf16(__uint_as_float(v[8 * q + 2]) + bias, __uint_as_float(v[8 * q + 3]) + bias);
-              w.z = pack_bf16(__uint_as_float(v[8 * q + 4]) + bias, __uint_as_float(v[8 * q + 5]) + bias);
-              w.w = pack_bf16(__uint_as_float(v[8 * q + 6]) + bias, __uint_as_float(v[8 * q + 7]) + bias);
-              d4[q] = w;
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(t_row + grp * 64 + c * 32, v);
+              tmem_ld_wait();
+              const float4* b4 = reinterpret_cast<const float4*>(vec + it * NT + half * HALF + grp * 64 + c * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float y[8];
+                if (MODE == G_INPROJ) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[q * 8 + j]) + rowv;
+                } else {
+                  const float4 ba = b4[2 * q], bb = b4[2 * q + 1];
+                  const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float x = __uint_as_float(v[q * 8 + j]) + bj[j];
+                    y[j] = (MODE == G_FC1) ? gelu_tanh(x) : (fmaxf(x, 0.f) + rowv);
+                  }
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + c * 64 + q * 16),
+                             "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])),
+                             "r"(pack_bf16(y[6], y[7]))
+                             : "memory");
+              }
             }
+            __syncwarp();
+            // T-layout coalesced store: 4 rows x 128 B per instruction
+            __nv_bfloat16* dst;
+            size_t pitch;
+            if (MODE == G_INPROJ) {
+              const int b = tok0 / p.L, l0 = tok0 % p.L;
+              dst = p.out_bf16 + ((size_t)b * 768 + it * kTileM + quad * 32 + trow0) * p.L + l0 + half * HALF + grp * 64 +
+                    piece * 8;
+              pitch = (size_t)p.L;
+            } else {
+              dst = p.out_bf16 + ((size_t)tok0 + quad * 32 + trow0) * 1024 + it * NT + half * HALF + grp * 64 + piece * 8;
+              pitch = 1024;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 w = *reinterpret_cast<const uint4*>(stg_t + i * 4 * kStagePitch);
+              *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * pitch) = w;
+            }
+            __syncwarp();
           }
         } else if (MODE == G_OUTPROJ || MODE == G_FC2) {
-          const size_t row = (size_t)tok0 + row_in_tile;
-          const float4* res4 = reinterpret_cast<const float4*>(p.resid + row * 256);
-          float4* h4 = p.h_out ? reinterpret_cast<float4*>(p.h_out + row * 256) : nullptr;
-          float sum = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
+          // ---- + bias + residual -> h (fp32), LayerNorm -> bf16 ------------------------------------------------
+          // Global I/O in the T layout (whole 128-byte lines per instruction); the residual of the next two
+          // column chunks is prefetched into registers (memory-level parallelism: these kernels are
+          // HBM-bound, 3-4.6 KB per token); x = acc + bias + residual goes back into the TMEM accumulator so
+          // the normalisation pass needs no second trip through L2.
+          float sum[8], sq[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+          const size_t row_t = (size_t)tok0 + quad * 32 + trow0;  // + 4 i
+          const int colbase = half * HALF + piece * 4;
+#pragma unroll
+          for (int c = 0; c < HALF / 32; ++c) {
+            float4 (&rc)[8] = (c & 1) ? rpre1 : rpre0;
             tmem_ld32(t_row + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 r = __ldg(res4 + c * 8 + q);
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias) + c * 8 + q);
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + q * 16), "r"(v[4 * q]),
+                           "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                           : "memory");
+            __syncwarp();
+            const int col = colbase + c * 32;
+            const float4 bb = *reinterpret_cast<const float4*>(vec + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4* sp = reinterpret_cast<float4*>(const_cast<uint8_t*>(stg_t) + i * 4 * kStagePitch);
+              const float4 a = *sp;
+              const float4 r = rc[i];
               float4 x;
-              x.x = __uint_as_float(v[4 * q + 0]) + bb.x + r.x;
-              x.y = __uint_as_float(v[4 * q + 1]) + bb.y + r.y;
-              x.z = __uint_as_float(v[4 * q + 2]) + bb.z + r.z;
-              x.w = __uint_as_float(v[4 * q + 3]) + bb.w + r.w;
-              sum += (x.x + x.y) + (x.z + x.w);
-              if (h4) h4[c * 8 + q] = x;
-              v[4 * q + 0] = __float_as_uint(x.x);
-              v[4 * q + 1] = __float_as_uint(x.y);
-              v[4 * q + 2] = __float_as_uint(x.z);
-              v[4 * q + 3] = __float_as_uint(x.w);
+              x.x = a.x + bb.x + r.x;
+              x.y = a.y + bb.y + r.y;
+              x.z = a.z + bb.z + r.z;
+              x.w = a.w + bb.w + r.w;
+              *reinterpret_cast<float4*>(p.h_out + (row_t + 4 * i) * 256 + col) = x;
+              *sp = x;
+              sum[i] += (x.x + x.y) + (x.z + x.w);
+              sq[i] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, sq[i]))));
             }
+            // prefetch the residual two chunks ahead (this tile), or the first chunks of my next tile
+            {
+              const int cn = c + 2;
+              if (cn < HALF / 32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  rc[i] = *reinterpret_cast<const float4*>(p.resid + (row_t + 4 * i) * 256 + colbase + cn * 32);
+              } else if (o + (int)gridDim.x < num_outer) {
+                const size_t nrow = (size_t)(o + gridDim.x) * kTileM + quad * 32 + trow0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  rc[i] = *reinterpret_cast<const float4*>(p.resid + (nrow + 4 * i) * 256 + colbase + (cn - HALF / 32) * 32);
+              }
+            }
+            __syncwarp();
+            // x back to the accumulator (row-owner layout)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(v[4 * q]), "=r"(v[4 * q + 1]), "=r"(v[4 * q + 2]), "=r"(v[4 * q + 3])
+                           : "r"(stg_own + q * 16)
+                           : "memory");
             tmem_st32(t_row + c * 32, v);
+            __syncwarp();
+          }
+          // row statistics: reduce over the 8 lanes sharing a row, then over the two column halves
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+              sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], d);
+              sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
+            }
+          }
+          float2* st = stats + tile_parity * 256;
+          if (piece == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st[half * 128 + quad * 32 + trow0 + 4 * i] = make_float2(sum[i], sq[i]);
           }
           tmem_st_wait();
-          const float mean = sum * (1.0f / 256.0f);
-          float var = 0.f;
+          named_bar_sync(1 + quad, 64);
+          const float2 sa = st[quad * 32 + lane], sb = st[128 + quad * 32 + lane];  // my own row (row-owner)
+          const float mean = (sa.x + sb.x) * (1.0f / 256.0f);
+          const float rstd = rsqrtf(fmaxf((sa.y + sb.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
+          for (int grp = 0; grp < HALF / 64; ++grp) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float d = __uint_as_float(v[j]) - mean;
-              var = fmaf(d, d, var);
-            }
-          }
-          const float rstd = rsqrtf(var * (1.0f / 256.0f) + 1e-5f);
-          uint4* u4 = reinterpret_cast<uint4*>(p.out_bf16 + row * 256);
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(t_row + grp * 64 + c * 32, v);
+              tmem_ld_wait();
+              const float4* g4 = reinterpret_cast<const float4*>(vec + 1024 + half * HALF + grp * 64 + c * 32);
+              const float4* b4 = reinterpret_cast<const float4*>(vec + 2048 + half * HALF + grp * 64 + c * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float y[8];
+              for (int q = 0; q < 4; ++q) {
+                const float4 ga = g4[2 * q], gb = g4[2 * q + 1], ba = b4[2 * q], bb2 = b4[2 * q + 1];
+                const float gj[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb2.x, bb2.y, bb2.z, bb2.w};
+                float y[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int col = c * 32 + q * 8 + j;
-                y[j] = fmaf((__uint_as_float(v[q * 8 + j]) - mean) * rstd, __ldg(p.ln_g + col), __ldg(p.ln_b + col));
+                for (int j = 0; j < 8; ++j) y[j] = fmaf((__uint_as_float(v[q * 8 + j]) - mean) * rstd, gj[j], bj[j]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + c * 64 + q * 16),
+                             "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])),
+                             "r"(pack_bf16(y[6], y[7]))
+                             : "memory");
               }
-              uint4 w;
-              w.x = pack_bf16(y[0], y[1]);
-              w.y = pack_bf16(y[2], y[3]);
-              w.z = pack_bf16(y[4], y[5]);
-              w.w = pack_bf16(y[6], y[7]);
-              u4[c * 4 + q] = w;
             }
-          }
-        } else if (MODE == G_FC1 || MODE == G_HEAD1) {
-          const size_t row = (size_t)tok0 + row_in_tile;
-          const float qv = (MODE == G_HEAD1) ? __ldg(p.qual + row) : 0.f;
-          uint4* g4 = reinterpret_cast<uint4*>(p.out_bf16 + row * 1024 + i * NT);
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
+            __syncwarp();
+            __nv_bfloat16* dst = p.out_bf16 + row_t * 256 + half * HALF + grp * 64 + piece * 8;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float y[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float x = __uint_as_float(v[q * 8 + j]) + __ldg(p.bias + i * NT + c * 32 + q * 8 + j);
-                y[j] = (MODE == G_FC1) ? gelu_tanh(x) : (fmaxf(x, 0.f) + qv);
-              }
-              uint4 w;
-              w.x = pack_bf16(y[0], y[1]);
-              w.y = pack_bf16(y[2], y[3]);
-              w.z = pack_bf16(y[4], y[5]);
-              w.w = pack_bf16(y[6], y[7]);
-              g4[c * 4 + q] = w;
+            for (int i = 0; i < 8; ++i) {
+              const uint4 w = *reinterpret_cast<const uint4*>(stg_t + i * 4 * kStagePitch);
+              *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * 256) = w;
             }
+            __syncwarp();
           }
+          tile_parity ^= 1;
         } else {  // G_HEAD2
-          const size_t row = (size_t)tok0 + row_in_tile;
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.r_in + row * 1024 + i * NT);
+          const size_t row_t = (size_t)tok0 + quad * 32 + trow0;
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < HALF / 32; ++c) {
             tmem_ld32(t_row + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rr = __ldg(r4 + c * 4 + q);
-              const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + q * 16), "r"(v[4 * q]),
+                           "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                           : "memory");
+            __syncwarp();
+            const int col = it * NT + half * HALF + c * 32 + piece * 4;
+            const float4 bb = *reinterpret_cast<const float4*>(vec + col);
+            const float4 wa = *reinterpret_cast<const float4*>(vec + 1024 + col);
+            const float4 wb = *reinterpret_cast<const float4*>(vec + 2048 + col);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int col = i * NT + c * 32 + q * 8 + j;
-                const uint32_t pr = rw[j >> 1];
-                const float rres = __uint_as_float((j & 1) ? (pr & 0xffff0000u) : (pr << 16));
-                const float ov = fmaxf(__uint_as_float(v[q * 8 + j]) + __ldg(p.bias + col) + rres, 0.f);
-                lg0 = fmaf(ov, __ldg(p.w3 + col), lg0);
-                lg1 = fmaf(ov, __ldg(p.w3 + 1024 + col), lg1);
+            for (int i = 0; i < 8; ++i) {
+              const float4 a = *reinterpret_cast<const float4*>(stg_t + i * 4 * kStagePitch);
+              const uint2 rr = __ldg(reinterpret_cast<const uint2*>(p.r_in + (row_t + 4 * i) * 1024 + col));
+              const float o0 = fmaxf(a.x + bb.x + __uint_as_float(rr.x << 16), 0.f);
+              const float o1 = fmaxf(a.y + bb.y + __uint_as_float(rr.x & 0xffff0000u), 0.f);
+              const float o2 = fmaxf(a.z + bb.z + __uint_as_float(rr.y << 16), 0.f);
+              const float o3 = fmaxf(a.w + bb.w + __uint_as_float(rr.y & 0xffff0000u), 0.f);
+              lg0[i] = fmaf(o0, wa.x, fmaf(o1, wa.y, fmaf(o2, wa.z, fmaf(o3, wa.w, lg0[i]))));
+              lg1[i] = fmaf(o0, wb.x, fmaf(o1, wb.y, fmaf(o2, wb.z, fmaf(o3, wb.w, lg1[i]))));
+            }
+            __syncwarp();
+          }
+          if (it == Tr::INNER - 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+              for (int d = 1; d < 8; d <<= 1) {
+                lg0[i] += __shfl_xor_sync(0xffffffffu, lg0[i], d);
+                lg1[i] += __shfl_xor_sync(0xffffffffu, lg1[i], d);
               }
             }
-          }
-          if (i == Tr::INNER - 1) {
-            lg0 += __ldg(p.b3);
-            lg1 += __ldg(p.b3 + 1);
-            if (p.logits) reinterpret_cast<float2*>(p.logits)[row] = make_float2(lg0, lg1);
-            if (p.labels) p.labels[row] = lg1 > lg0 ? 1 : 0;
+            float2* st = stats + tile_parity * 256;
+            if (half == 1 && piece == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) st[quad * 32 + trow0 + 4 * i] = make_float2(lg0[i], lg1[i]);
+            }
+            named_bar_sync(1 + quad, 64);
+            if (half == 0 && piece == 0) {
+              const float b30 = __ldg(p.b3), b31 = __ldg(p.b3 + 1);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 o2 = st[quad * 32 + trow0 + 4 * i];
+                const float l0 = lg0[i] + o2.x + b30, l1 = lg1[i] + o2.y + b31;
+                const size_t row = row_t + 4 * i;
+                if (p.logits) reinterpret_cast<float2*>(p.logits)[row] = make_float2(l0, l1);
+                if (p.labels) p.labels[row] = l1 > l0 ? 1 : 0;
+              }
+            }
+            tile_parity ^= 1;
           }
         }
         tc_fence_before();
@@ -342,7 +486,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int MODE> static size_t smem_bytes() {
   using Tr = Traits<MODE>;
-  return (size_t)kStages * (kTileM * 128 + Tr::NT * 128) + 1024 + 256;
+  return (size_t)Tr::STAGES * (kTileM * 128 + Tr::NT * 128) + kEpiWarps * kStageBytes + kVecFloats * 4 + 2 * 2 * 128 * 8 +
+         1024 + 256;
 }
 
 template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
@@ -355,7 +500,7 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
   static const int kinds[6] = {K_INPROJ, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2};
   ProfScope prof(ctx, kinds[MODE]);
-  gemm_kernel<MODE><<<grid, 256, smem, ctx->stream>>>(a, b, p);
+  gemm_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(a, b, p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }

@@ -409,7 +409,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     p = gp;
     p.bias = lw.b_fc2;
     p.resid = hB;
-    p.h_out = (l + 1 < kLayers) ? hA : nullptr;
+    p.h_out = hA;  // (the last layer's value is not consumed again, but the epilogue stages through it)
     p.ln_g = (l + 1 < kLayers) ? w->layer[l + 1].ln1_g : w->lnf_g;
     p.ln_b = (l + 1 < kLayers) ? w->layer[l + 1].ln1_b : w->lnf_b;
     p.out_bf16 = u;
