@@ -5,6 +5,9 @@
 #include "common.cuh"
 #include "fftconv.h"
 #include "gemm.h"
+#include "toeplitz.h"
+
+#include <stdlib.h>
 
 #include <math.h>
 #include <string.h>
@@ -27,6 +30,8 @@ struct LayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   float* k = nullptr;  // [256][Lmax] implicit filter, evaluated once
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
+  __nv_bfloat16* toep = nullptr;  // [256][kToepMaxBlocks][128][128] Toeplitz blocks of k' (built on first use)
+  CUtensorMap tm_toep;
   CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
 };
 
@@ -310,6 +315,32 @@ static int ensure_fft_size(dcb200_ctx* ctx, dcb200_weights* w, int N) {
   return DCB200_OK;
 }
 
+// Toeplitz block tables of all layers (1 GiB for 4 layers x 256 channels x 32 blocks), built on first use
+static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w) {
+  if (w->layer[0].toep) return DCB200_OK;
+  for (int l = 0; l < kLayers; ++l) {
+    void* t = nullptr;
+    const size_t bytes = (size_t)kD * kToepMaxBlocks * 128 * 128 * 2;
+    DCB_CUDA(cudaMalloc(&t, bytes));
+    w->allocs.push_back(t);
+    DCB_CHECK(launch_toeplitz_build(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, kToepMaxBlocks,
+                                    static_cast<__nv_bfloat16*>(t)));
+    DCB_CHECK(make_tmap_2d(&w->layer[l].tm_toep, t, (uint64_t)kD * kToepMaxBlocks * 128, 128, 128));
+    w->layer[l].toep = static_cast<__nv_bfloat16*>(t);
+  }
+  return DCB200_OK;
+}
+
+// Which long-convolution kernel: block-Toeplitz tensor-core GEMMs up to 4096 tokens, shared-memory FFT above.
+// DCB200_CONV=fft|toeplitz overrides (used by the tests to cover both kernels at the same size).
+static bool use_toeplitz(int L) {
+  const char* e = getenv("DCB200_CONV");
+  if (e && !strcmp(e, "fft")) return false;
+  if (L > kToepMaxBlocks * 128) return false;
+  if (e && !strcmp(e, "toeplitz")) return true;
+  return true;
+}
+
 int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
                    float* logits, uint8_t* labels, int stop_stage) {
   int stage = 0;
@@ -322,13 +353,18 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     set_error("weights live on device %d, ctx on %d", w->device, ctx->device);
     return DCB200_EINVAL;
   }
+  const bool toep = use_toeplitz(L);
   int N = 256;
   while (N < 2 * L) N <<= 1;
-  if (conv_smem_bytes(N, L) > 227 * 1024) {
-    set_error("L=%d: long-read (> 8192 tokens) convolution path is not built yet", L);
-    return DCB200_EINVAL;
+  if (!toep) {
+    if (conv_smem_bytes(N, L) > 227 * 1024) {
+      set_error("L=%d: long-read (> 8192 tokens) convolution path is not built yet", L);
+      return DCB200_EINVAL;
+    }
+    DCB_CHECK(ensure_fft_size(ctx, w, N));
+  } else {
+    DCB_CHECK(ensure_toeplitz(ctx, w));
   }
-  DCB_CHECK(ensure_fft_size(ctx, w, N));
   const size_t T = (size_t)B * L;
   DevBuf& bhA = ctx->buf("act_hA");
   DevBuf& bhB = ctx->buf("act_hB");
@@ -349,6 +385,17 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   __nv_bfloat16* y = by.as<__nv_bfloat16>();
   __nv_bfloat16* g = bg.as<__nv_bfloat16>();
 
+  __nv_bfloat16 *vv = nullptr, *gate = nullptr;
+  CUtensorMap tm_vv;
+  if (toep) {
+    DevBuf& bvv = ctx->buf("act_vv");
+    DevBuf& bgt = ctx->buf("act_gate");
+    DCB_CHECK(bvv.reserve(T * kD * 2));
+    DCB_CHECK(bgt.reserve(T * kD * 2));
+    vv = bvv.as<__nv_bfloat16>();
+    gate = bgt.as<__nv_bfloat16>();
+    DCB_CHECK(make_tmap_3d_rows(&tm_vv, vv, B, kD, L));
+  }
   CUtensorMap tm_u, tm_y, tm_g;
   DCB_CHECK(make_tmap_2d(&tm_u, u, T, kD, 128));
   DCB_CHECK(make_tmap_3d_cm(&tm_y, y, B, kD, L));
@@ -377,17 +424,30 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     DCB_CHECK(launch_gemm(ctx, G_INPROJ, lw.tm_in, tm_u, p));
     DCB_STAGE_DONE();
 
-    ConvParams cp;
-    cp.z = z;
-    cp.y = y;
-    cp.short_w = lw.short_w;
-    cp.short_b = lw.short_b;
-    cp.KF = lw.KF[N];
-    cp.tw = w->tw[N];
-    cp.B = B;
-    cp.L = L;
-    cp.plan = plan;
-    DCB_CHECK(launch_fftconv(ctx, cp));
+    if (toep) {
+      DCB_CHECK(launch_shortconv_gate(ctx, z, lw.short_w, lw.short_b, B, L, vv, gate));
+      GemmParams tp = gp;
+      tp.B = B;
+      tp.nb = L / 128;
+      tp.n_rt = (B + 127) / 128;
+      tp.nb_max = kToepMaxBlocks;
+      tp.num_outer = tp.nb * 256 * tp.n_rt;
+      tp.gate = gate;
+      tp.out_bf16 = y;
+      DCB_CHECK(launch_gemm(ctx, G_TOEP, tm_vv, lw.tm_toep, tp));
+    } else {
+      ConvParams cp;
+      cp.z = z;
+      cp.y = y;
+      cp.short_w = lw.short_w;
+      cp.short_b = lw.short_b;
+      cp.KF = lw.KF[N];
+      cp.tw = w->tw[N];
+      cp.B = B;
+      cp.L = L;
+      cp.plan = plan;
+      DCB_CHECK(launch_fftconv(ctx, cp));
+    }
     DCB_STAGE_DONE();
 
     p = gp;

@@ -77,8 +77,15 @@ def close(name, got, want, atol, rtol):
     assert worst <= 0, f"{name}: max err {err.max().item()} (|ref| mean {want.abs().mean().item()})"
 
 
-@pytest.mark.parametrize("B,L", [(4, 256), (3, 384)])
-def test_layer0_stage_by_stage(ref, gpu, B, L):
+@pytest.fixture(params=["toeplitz", "fft"])
+def conv_kind(request, monkeypatch):
+    """Both long-convolution kernels (block-Toeplitz tcgen05 GEMMs / shared-memory FFT) at the same sizes."""
+    monkeypatch.setenv("DCB200_CONV", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("B,L", [(4, 256), (3, 384), (130, 640)])
+def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
     rng = np.random.default_rng(100 + B)
     ids, q = make_batch(rng, B, L)
     tok = ids.to(torch.uint8).cuda()
@@ -106,7 +113,8 @@ def test_layer0_stage_by_stage(ref, gpu, B, L):
         x0, x1, v = zc.split(256, dim=1)
         k = lay.mixer.filter_fn.filter(L)[0].transpose(0, 1)
         y_ref = H.fftconv_ref(v * x1, k, lay.mixer.filter_fn.bias) * x0
-        close("hyena_conv", y, y_ref, 2e-2 * y_ref.abs().mean().item() + 1e-3, 1.5e-2)
+        # bf16 z in, bf16 y out (and bf16 filter taps on the Toeplitz path): ~0.4 % of the local signal scale
+        close("hyena_conv", y, y_ref, 3e-2 * y_ref.pow(2).mean().sqrt().item() + 1e-3, 2e-2)
         # stage 3: out_proj + residual + LN2
         run_debug(gpu, tok, qd, 3)
         hB = read_ws(gpu, "act_hB", (B, L, 256), "f32")
@@ -128,8 +136,8 @@ def test_layer0_stage_by_stage(ref, gpu, B, L):
         close("ln1_next", u2, bb.layers[1].norm1(hA2), 1e-2, 1e-2)
 
 
-@pytest.mark.parametrize("B,L", [(4, 256), (5, 1024), (2, 2048), (16, 640)])
-def test_forward_logits_and_labels(ref, gpu, B, L):
+@pytest.mark.parametrize("B,L", [(4, 256), (5, 1024), (2, 2048), (16, 640), (1, 4096)])
+def test_forward_logits_and_labels(ref, gpu, B, L, conv_kind):
     rng = np.random.default_rng(7 * B + L)
     ids, q = make_batch(rng, B, L)
     with torch.no_grad():
@@ -148,6 +156,15 @@ def test_forward_logits_and_labels(ref, gpu, B, L):
     tok = ids.to(torch.uint8).cuda()
     lg, lb = gpu.forward_tokens(tok, q.cuda(), True, True)
     assert torch.equal(lb.bool(), lg[..., 1] > lg[..., 0])
+
+
+def test_forward_long_read_uses_fft(ref, gpu):
+    rng = np.random.default_rng(12)
+    ids, q = make_batch(rng, 2, 4224)        # > 4096 tokens: shared-memory FFT path
+    with torch.no_grad():
+        want = ref(ids, q)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    close("logits L=4224", got, want, LOGIT_ATOL_VS_FP32, 0.0)
 
 
 def test_forward_arbitrary_length_is_right_filled(ref, gpu):
