@@ -40,7 +40,6 @@ template <> struct Traits<G_FC1>     { static constexpr int K = 256,  NT = 256, 
 template <> struct Traits<G_FC2>     { static constexpr int K = 1024, NT = 256, INNER = 1, STAGES = 3; static constexpr bool A_MN = false; };
 template <> struct Traits<G_HEAD1>   { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
 template <> struct Traits<G_HEAD2>   { static constexpr int K = 1024, NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
-template <> struct Traits<G_TOEP>    { static constexpr int K = 128,  NT = 128, INNER = 1, STAGES = 4; static constexpr bool A_MN = false; };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -138,22 +137,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       for (int o = blockIdx.x; o < num_outer; o += gridDim.x) {
         const int tok0 = o * kTileM;
-        // TOEP work item -> (output block j, channel c, row tile rt); longest K loops first
-        const int t_rt = (MODE == G_TOEP) ? o % p.n_rt : 0;
-        const int t_c = (MODE == G_TOEP) ? (o / p.n_rt) % 256 : 0;
-        const int t_j = (MODE == G_TOEP) ? p.nb - 1 - o / (p.n_rt * 256) : 0;
-        const int nk = (MODE == G_TOEP) ? 2 * (t_j + 1) : KCH;
+        constexpr int nk = KCH;
         for (int i = 0; i < Tr::INNER; ++i) {
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             const uint32_t b_dst = a_dst + A_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            if (MODE == G_TOEP) {
-              const int ib = kc >> 1, kh = kc & 1;  // input block, 64-wide half of it
-              tma_load_3d(a_dst, &tmA, full_bar(stage), ib * 128 + kh * 64, t_c, t_rt * 128);
-              tma_load_2d(b_dst, &tmB, full_bar(stage), kh * 64, (t_c * p.nb_max + (t_j - ib)) * 128);
-            } else if (MODE == G_INPROJ) {
+            if (MODE == G_INPROJ) {
               tma_load_2d(a_dst, &tmA, full_bar(stage), kc * kBlockK, i * kTileM);  // W_in rows (channels)
               tma_load_2d(b_dst, &tmB, full_bar(stage), kc * kBlockK, tok0);        // tokens
             } else {
@@ -183,7 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int o = blockIdx.x; o < num_outer; o += gridDim.x) {
-        const int nk = (MODE == G_TOEP) ? 2 * (p.nb - o / (p.n_rt * 256)) : KCH;
+        constexpr int nk = KCH;
         for (int i = 0; i < Tr::INNER; ++i) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tc_fence_after();
@@ -419,36 +410,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
           }
           tile_parity ^= 1;
-        } else if (MODE == G_TOEP) {
-          // ---- y = conv * gate -> bf16 channel-major; rows are batch rows, columns tokens -----------------------
-          const int t_rt = o % p.n_rt, t_c = (o / p.n_rt) % 256, t_j = p.nb - 1 - o / (p.n_rt * 256);
-          const int brow = t_rt * 128 + quad * 32 + trow0;  // + 4 i
-#pragma unroll 1
-          for (int c = 0; c < HALF / 32; ++c) {
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + q * 16), "r"(v[4 * q]),
-                           "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
-                           : "memory");
-            __syncwarp();
-            const int tcol = t_j * 128 + half * HALF + c * 32 + piece * 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int b = brow + 4 * i;
-              if (b < p.B) {
-                const float4 a = *reinterpret_cast<const float4*>(stg_t + i * 4 * kStagePitch);
-                const size_t off = ((size_t)b * 256 + t_c) * p.L + tcol;
-                const uint2 gg = __ldg(reinterpret_cast<const uint2*>(p.gate + off));
-                uint2 w;
-                w.x = pack_bf16(a.x * __uint_as_float(gg.x << 16), a.y * __uint_as_float(gg.x & 0xffff0000u));
-                w.y = pack_bf16(a.z * __uint_as_float(gg.y << 16), a.w * __uint_as_float(gg.y & 0xffff0000u));
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) = w;
-              }
-            }
-            __syncwarp();
-          }
         } else {  // G_HEAD2
           const size_t row_t = (size_t)tok0 + quad * 32 + trow0;
 #pragma unroll 1
@@ -539,7 +500,7 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
     configured = true;
   }
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
-  static const int kinds[7] = {K_INPROJ, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_TOEP};
+  static const int kinds[6] = {K_INPROJ, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2};
   ProfScope prof(ctx, kinds[MODE]);
   gemm_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(a, b, p);
   DCB_LAUNCH_CHECK(ctx);
@@ -554,7 +515,6 @@ int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorM
     case G_FC2: return launch_mode<G_FC2>(ctx, a, b, p);
     case G_HEAD1: return launch_mode<G_HEAD1>(ctx, a, b, p);
     case G_HEAD2: return launch_mode<G_HEAD2>(ctx, a, b, p);
-    case G_TOEP: return launch_mode<G_TOEP>(ctx, a, b, p);
   }
   set_error("bad gemm mode %d", mode);
   return DCB200_EINVAL;

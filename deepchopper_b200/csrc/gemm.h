@@ -7,7 +7,7 @@ struct dcb200_ctx;
 
 namespace dcb {
 
-enum GemmMode { G_INPROJ = 0, G_OUTPROJ = 1, G_FC1 = 2, G_FC2 = 3, G_HEAD1 = 4, G_HEAD2 = 5, G_TOEP = 6 };
+enum GemmMode { G_INPROJ = 0, G_OUTPROJ = 1, G_FC1 = 2, G_FC2 = 3, G_HEAD1 = 4, G_HEAD2 = 5 };
 
 struct GemmParams {
   int T;          // tokens = B * L (multiple of 128)
@@ -25,12 +25,6 @@ struct GemmParams {
   const float* b3;          // HEAD2: [2]
   float* logits;            // HEAD2: [T,2] or null
   uint8_t* labels;          // HEAD2: [T] or null
-  // TOEP (long convolution as block-Toeplitz GEMMs): y[b,c,t] = gate[b,c,t] * sum_s vv[b,c,s] * k'_c[t-s]
-  int B;                    // batch rows
-  int nb;                   // L / 128 token blocks
-  int n_rt;                 // ceil(B / 128) row tiles
-  int nb_max;               // blocks per channel in the Toeplitz tile table
-  const __nv_bfloat16* gate;  // [B,256,L] short-conv'ed x0
 };
 
 int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p);

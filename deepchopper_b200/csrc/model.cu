@@ -30,8 +30,7 @@ struct LayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   float* k = nullptr;  // [256][Lmax] implicit filter, evaluated once
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
-  __nv_bfloat16* toep = nullptr;  // [256][kToepMaxBlocks][128][128] Toeplitz blocks of k' (built on first use)
-  CUtensorMap tm_toep;
+  __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
   CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
 };
 
@@ -315,17 +314,14 @@ static int ensure_fft_size(dcb200_ctx* ctx, dcb200_weights* w, int N) {
   return DCB200_OK;
 }
 
-// Toeplitz block tables of all layers (1 GiB for 4 layers x 256 channels x 32 blocks), built on first use
+// Toeplitz core-matrix tables of all layers (17 MB each), built on first use
 static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w) {
   if (w->layer[0].toep) return DCB200_OK;
   for (int l = 0; l < kLayers; ++l) {
     void* t = nullptr;
-    const size_t bytes = (size_t)kD * kToepMaxBlocks * 128 * 128 * 2;
-    DCB_CUDA(cudaMalloc(&t, bytes));
+    DCB_CUDA(cudaMalloc(&t, toeplitz_table_bytes()));
     w->allocs.push_back(t);
-    DCB_CHECK(launch_toeplitz_build(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, kToepMaxBlocks,
-                                    static_cast<__nv_bfloat16*>(t)));
-    DCB_CHECK(make_tmap_2d(&w->layer[l].tm_toep, t, (uint64_t)kD * kToepMaxBlocks * 128, 128, 128));
+    DCB_CHECK(launch_toeplitz_table(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, static_cast<__nv_bfloat16*>(t)));
     w->layer[l].toep = static_cast<__nv_bfloat16*>(t);
   }
   return DCB200_OK;
@@ -336,7 +332,7 @@ static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w) {
 static bool use_toeplitz(int L) {
   const char* e = getenv("DCB200_CONV");
   if (e && !strcmp(e, "fft")) return false;
-  if (L > kToepMaxBlocks * 128) return false;
+  if (L > kToepMaxL) return false;
   if (e && !strcmp(e, "toeplitz")) return true;
   return true;
 }
@@ -386,7 +382,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   __nv_bfloat16* g = bg.as<__nv_bfloat16>();
 
   __nv_bfloat16 *vv = nullptr, *gate = nullptr;
-  CUtensorMap tm_vv;
+  CUtensorMap tm_vv, tm_gate, tm_yr;
   if (toep) {
     DevBuf& bvv = ctx->buf("act_vv");
     DevBuf& bgt = ctx->buf("act_gate");
@@ -395,6 +391,8 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     vv = bvv.as<__nv_bfloat16>();
     gate = bgt.as<__nv_bfloat16>();
     DCB_CHECK(make_tmap_3d_rows(&tm_vv, vv, B, kD, L));
+    DCB_CHECK(make_tmap_3d_rows(&tm_gate, gate, B, kD, L));
+    DCB_CHECK(make_tmap_3d_rows(&tm_yr, y, B, kD, L));
   }
   CUtensorMap tm_u, tm_y, tm_g;
   DCB_CHECK(make_tmap_2d(&tm_u, u, T, kD, 128));
@@ -426,15 +424,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
 
     if (toep) {
       DCB_CHECK(launch_shortconv_gate(ctx, z, lw.short_w, lw.short_b, B, L, vv, gate));
-      GemmParams tp = gp;
-      tp.B = B;
-      tp.nb = L / 128;
-      tp.n_rt = (B + 127) / 128;
-      tp.nb_max = kToepMaxBlocks;
-      tp.num_outer = tp.nb * 256 * tp.n_rt;
-      tp.gate = gate;
-      tp.out_bf16 = y;
-      DCB_CHECK(launch_gemm(ctx, G_TOEP, tm_vv, lw.tm_toep, tp));
+      DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, tm_vv, tm_gate, tm_yr, B, L));
     } else {
       ConvParams cp;
       cp.z = z;

@@ -1,28 +1,300 @@
 // Tensor-core form of the Hyena long convolution for L <= 4096:
-//   y[b,c,t] = x0c[b,c,t] * sum_{s<=t} vv[b,c,s] * k'_c[t-s],   vv = sc(v) * sc(x1),  x0c = sc(x0),  k'[0] = k[0] + D
-// The causal convolution of one channel is a lower-triangular Toeplitz matrix; cut into 128x128 blocks
-// it is nb(nb+1)/2 dense bf16 GEMM tiles per 128 batch rows, and block (j,i) only depends on d = j-i.
-// The blocks T_d[t',s'] = k'[128 d + t' - s'] are materialised once per weight set (bf16, K-major) and
-// streamed by TMA as the B operand of gemm_kernel<G_TOEP>; the A operand is vv read channel-major.
-// At L = 1-2k this is 10-20x less time than the fp32 shared-memory FFT (which stays for longer reads).
+//   y[b,c,t] = gate[b,c,t] * sum_{s<=t} vv[b,c,s] * k'_c[t-s],   vv = sc(v) * sc(x1),  gate = sc(x0),  k'[0] = k[0] + D
+//
+// Per channel the causal convolution is a GEMM  Y[b, t] = sum_s V[b, s] K[s, t]  with a Toeplitz K.  One CTA owns a
+// work item (channel c, 128 batch rows): A = V tiles streamed by TMA (K-major, 128B swizzle), D = 128 x 256 fp32
+// accumulators in TMEM (two of them, so the epilogue of one output tile overlaps the MMAs of the next).
+//
+// The Toeplitz operand is never materialised as tiles.  With the accumulator columns in REVERSED token order
+// (column n <-> token t_hi - n) the B operand entry for (column n, k-index s') is k'[Q - n - s'] - it depends on
+// n + s' only.  In the no-swizzle K-major UMMA layout a core matrix is 8 rows x 16 bytes, and the core matrix at
+// (n/8 = a, s'/8 = b) then depends on a + b only, so ONE array of (L/8 + 32) core matrices
+//     E[i][r][c] = k'[8 i + 7 - r - c]           (128 bytes per i, stored by descending i, zero for negative taps)
+// with LBO = SBO = 128 bytes serves every (output tile, input block) pair of the channel: the descriptor start
+// address selects Q.  E is 16 L + 4096 bytes per channel (20 KB at L = 1024) and is bulk-copied into shared memory
+// once per work item, so the kernel's global traffic is the algorithmic minimum: read vv and gate, write y.
+// Causality (s > t) falls out of the zero taps.
+//
+//   warp 0   producer: E bulk copy per item + A tiles (3-D TMA box 64 tokens x 1 channel x 128 rows)
+//   warp 1   MMA issuer (tcgen05.mma M=128, N=256 / 128 on the diagonal block, K=16)
+//   warp 2   TMEM allocator
+//   warp 3   gate-tile loader (TMA, same box shape)
+//   warps 4-11 epilogue: tcgen05.ld, multiply by the gate tile IN PLACE in its swizzled smem slot, TMA store
 #include "common.cuh"
+#include "gemm.h"
+#include "ptx.cuh"
 #include "toeplitz.h"
 
 namespace dcb {
 
-__global__ void __launch_bounds__(256) toeplitz_build_kernel(const float* __restrict__ k, int k_stride, int k_len,
-                                                             const float* __restrict__ D, int nb_max,
-                                                             __nv_bfloat16* __restrict__ T) {
-  const int d = blockIdx.x, c = blockIdx.y;
-  __nv_bfloat16* dst = T + ((size_t)c * nb_max + d) * 128 * 128;
+using namespace ptx;
+
+constexpr int kTzThreads = 384;
+constexpr int kTzAStages = 6;   // 16 KB each: 128 rows x 64 tokens
+constexpr int kTzGSlots = 3;    // 16 KB each
+constexpr int kTzZeroChunks = 32;
+constexpr uint32_t kTzBox = 128 * 128;  // bytes of one TMA box
+
+// E table: [256 channels][kToepMaxL/8 + 32 chunks][8 rows][8 cols] bf16, chunk position p <-> i = kToepMaxL/8 - 1 - p
+__global__ void __launch_bounds__(256) toeplitz_table_kernel(const float* __restrict__ k, int k_stride, int k_len,
+                                                             const float* __restrict__ D, __nv_bfloat16* __restrict__ E) {
+  constexpr int P = kToepMaxL / 8 + kTzZeroChunks;
+  const int c = blockIdx.y;
   const float* kc = k + (size_t)c * k_stride;
-  for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
-    const int tp = idx >> 7, sp = idx & 127;
-    const int u = 128 * d + tp - sp;
+  __nv_bfloat16* dst = E + (size_t)c * P * 64;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P * 64; idx += gridDim.x * blockDim.x) {
+    const int p = idx >> 6, r = (idx >> 3) & 7, cc = idx & 7;
+    const int i = kToepMaxL / 8 - 1 - p;
+    const int u = 8 * i + 7 - r - cc;
     float v = 0.f;
     if (u >= 0 && u < k_len) v = kc[u];
     if (u == 0) v += D[c];
     dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+struct ToepParams {
+  const __nv_bfloat16* E;  // table base
+  int L;                   // padded length (multiple of 128, <= kToepMaxL)
+  int n_rt;                // ceil(B / 128)
+  int n_items;             // 256 * n_rt
+  int nE;                  // E buffers in smem (2 when they fit, else 1)
+};
+
+__device__ __forceinline__ uint32_t tz_pack(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kTzThreads, 1)
+toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG,
+                const __grid_constant__ CUtensorMap tmY, const ToepParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t e_bytes = (uint32_t)(p.L / 8 + kTzZeroChunks) * 128u;
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t g_base = a_base + kTzAStages * kTzBox;
+  const uint32_t e_base = g_base + kTzGSlots * kTzBox;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (kTzAStages + kTzGSlots) * kTzBox + (size_t)p.nE * e_bytes);
+  // bars: afull[S] aempty[S] gfull[G] gempty[G] efull[2] eempty[2] tfull[2] tempty[2]
+  const uint32_t bar_base = smem_u32(bars);
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (kTzAStages + s); };
+  auto gfull = [&](int s) { return bar_base + 8u * (2 * kTzAStages + s); };
+  auto gempty = [&](int s) { return bar_base + 8u * (2 * kTzAStages + kTzGSlots + s); };
+  auto efull = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + s); };
+  auto eempty = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + 2 + s); };
+  auto tfull = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + 4 + s); };
+  auto tempty = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + 6 + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTzAStages + 2 * kTzGSlots + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmG);
+    prefetch_tmap(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTzAStages; ++s) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < kTzGSlots; ++s) {
+      mbar_init(gfull(s), 1);
+      mbar_init(gempty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(efull(s), 1);
+      mbar_init(eempty(s), 1);
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int L = p.L;
+  const int n_tiles = (L + 255) / 256;
+
+  if (warp == 0) {
+    // ===== producer: E per item, A tiles =====
+    if (lane == 0) {
+      int stage = 0, eb = 0;
+      uint32_t phase = 0, ephase = 0;
+      const __nv_bfloat16* e_src0 = p.E + (size_t)((kToepMaxL - L) / 8) * 64;
+      for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
+        const int c = o / p.n_rt, rt = o % p.n_rt;
+        mbar_wait(eempty(eb), ephase ^ 1);
+        mbar_arrive_expect_tx(efull(eb), e_bytes);
+        bulk_load_1d(e_base + eb * e_bytes, e_src0 + (size_t)c * (kToepMaxL / 8 + kTzZeroChunks) * 64, e_bytes, efull(eb));
+        if (++eb == p.nE) {
+          eb = 0;
+          ephase ^= 1;
+        }
+        for (int J = 0; J < n_tiles; ++J) {
+          const int t_hi = min(256 * J + 255, L - 1);
+          const int nkc = 2 * (t_hi / 128 + 1);  // 64-token chunks of the input blocks 0..t_hi/128
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(aempty(stage), phase ^ 1);
+            mbar_arrive_expect_tx(afull(stage), kTzBox);
+            tma_load_3d(a_base + stage * kTzBox, &tmV, afull(stage), kc * 64, c, rt * 128);
+            if (++stage == kTzAStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0, eb = 0, acc = 0;
+      uint32_t phase = 0, ephase = 0, acc_phase = 0;
+      for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
+        mbar_wait(efull(eb), ephase);
+        const uint32_t e_addr = e_base + eb * e_bytes;
+        for (int J = 0; J < n_tiles; ++J) {
+          const int t_hi = min(256 * J + 255, L - 1);
+          const int ntile = t_hi - 256 * J + 1;  // 256 or 128
+          const int ilast = t_hi / 128;
+          const int q0 = (t_hi - 7) / 8;         // q of (i = 0, half 0, k = 0)
+          mbar_wait(tempty(acc), acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          const uint32_t idesc_full = make_idesc_bf16(128, ntile, false, false);
+          const uint32_t idesc_diag = make_idesc_bf16(128, 128, false, false);
+          for (int i = 0; i <= ilast; ++i) {
+            const uint32_t idesc = (i == ilast) ? idesc_diag : idesc_full;
+            for (int hh = 0; hh < 2; ++hh) {
+              mbar_wait(afull(stage), phase);
+              tc_fence_after();
+              const uint32_t a_addr = a_base + stage * kTzBox;
+              const int q = q0 - 16 * i - 8 * hh;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc = make_desc_sw128(a_addr + k * 32, 16, 1024);
+                const uint64_t bdesc = make_desc_nosw(e_addr + (uint32_t)(L / 8 - 1 - (q - 2 * k)) * 128u, 128, 128);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, (i | hh | k) ? 1u : 0u);
+              }
+              umma_commit(aempty(stage));
+              if (++stage == kTzAStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          umma_commit(tfull(acc));
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        umma_commit(eempty(eb));  // E buffer reusable once every MMA of this item has retired
+        if (++eb == p.nE) {
+          eb = 0;
+          ephase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== gate tile loader =====
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t gphase = 0;
+      for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
+        const int c = o / p.n_rt, rt = o % p.n_rt;
+        for (int t0 = 0; t0 < L; t0 += 64) {
+          mbar_wait(gempty(slot), gphase ^ 1);
+          mbar_arrive_expect_tx(gfull(slot), kTzBox);
+          tma_load_3d(g_base + slot * kTzBox, &tmG, gfull(slot), t0, c, rt * 128);
+          if (++slot == kTzGSlots) {
+            slot = 0;
+            gphase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;  // which 32 tokens of a 64-token box
+    const int row = quad * 32 + lane;
+    const bool storer = (threadIdx.x == 128);
+    int slot = 0, acc = 0, prev_slot = -1;
+    uint32_t gphase = 0, acc_phase = 0;
+    uint32_t v[32];
+    for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
+      const int c = o / p.n_rt, rt = o % p.n_rt;
+      for (int J = 0; J < n_tiles; ++J) {
+        const int t_hi = min(256 * J + 255, L - 1);
+        const int ntile = t_hi - 256 * J + 1;
+        mbar_wait(tfull(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+        for (int x = 0; x < ntile / 64; ++x) {
+          mbar_wait(gfull(slot), gphase);
+          const int c0 = ntile - 64 * x - 32 * half - 32;  // accumulator columns of my 32 tokens (reversed order)
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          const uint32_t rowaddr = g_base + slot * kTzBox + row * 128;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t addr = rowaddr + (uint32_t)(((4 * half + jj) ^ (row & 7)) * 16);
+            uint32_t g0, g1, g2, g3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(addr) : "memory");
+            const int m = 31 - 8 * jj;  // token 8 jj + i of my span <-> v[m - i]
+            const uint32_t w0 = tz_pack(__uint_as_float(v[m]) * __uint_as_float(g0 << 16),
+                                        __uint_as_float(v[m - 1]) * __uint_as_float(g0 & 0xffff0000u));
+            const uint32_t w1 = tz_pack(__uint_as_float(v[m - 2]) * __uint_as_float(g1 << 16),
+                                        __uint_as_float(v[m - 3]) * __uint_as_float(g1 & 0xffff0000u));
+            const uint32_t w2 = tz_pack(__uint_as_float(v[m - 4]) * __uint_as_float(g2 << 16),
+                                        __uint_as_float(v[m - 5]) * __uint_as_float(g2 & 0xffff0000u));
+            const uint32_t w3 = tz_pack(__uint_as_float(v[m - 6]) * __uint_as_float(g3 << 16),
+                                        __uint_as_float(v[m - 7]) * __uint_as_float(g3 & 0xffff0000u));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (storer) {
+            tma_store_3d(&tmY, g_base + slot * kTzBox, 256 * J + 64 * x, c, rt * 128);
+            bulk_commit();
+            if (prev_slot >= 0) {
+              bulk_wait_read<1>();  // the previous store has finished reading its slot
+              mbar_arrive(gempty(prev_slot));
+            }
+            prev_slot = slot;
+          }
+          if (++slot == kTzGSlots) {
+            slot = 0;
+            gphase ^= 1;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    if (storer) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -79,10 +351,39 @@ __global__ void __launch_bounds__(256) shortconv_gate_kernel(const __nv_bfloat16
   }
 }
 
-int launch_toeplitz_build(dcb200_ctx* ctx, const float* k, int k_stride, int k_len, const float* D, int nb_max,
-                          __nv_bfloat16* T) {
-  dim3 grid(nb_max, 256);
-  toeplitz_build_kernel<<<grid, 256, 0, ctx->stream>>>(k, k_stride, k_len, D, nb_max, T);
+
+int launch_toeplitz_table(dcb200_ctx* ctx, const float* k, int k_stride, int k_len, const float* D, __nv_bfloat16* E) {
+  dim3 grid(8, 256);
+  toeplitz_table_kernel<<<grid, 256, 0, ctx->stream>>>(k, k_stride, k_len, D, E);
+  DCB_LAUNCH_CHECK(ctx);
+  return DCB200_OK;
+}
+
+size_t toeplitz_table_bytes() { return (size_t)256 * (kToepMaxL / 8 + kTzZeroChunks) * 128; }
+
+int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, const CUtensorMap& tm_vv, const CUtensorMap& tm_gate,
+                         const CUtensorMap& tm_y, int B, int L) {
+  if (L % 128 != 0 || L > kToepMaxL || L <= 0) {
+    set_error("toeplitz conv: L=%d must be a multiple of 128 and <= %d", L, kToepMaxL);
+    return DCB200_EINVAL;
+  }
+  ToepParams p;
+  p.E = E;
+  p.L = L;
+  p.n_rt = (B + 127) / 128;
+  p.n_items = 256 * p.n_rt;
+  const size_t e_bytes = (size_t)(L / 8 + kTzZeroChunks) * 128;
+  const size_t fixed = (size_t)(kTzAStages + kTzGSlots) * kTzBox + 1024 + 512;
+  p.nE = (fixed + 2 * e_bytes <= 227 * 1024) ? 2 : 1;
+  const size_t want = fixed + p.nE * e_bytes;
+  static size_t configured = 0;
+  if (want > configured) {
+    DCB_CUDA(cudaFuncSetAttribute(toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+    configured = want;
+  }
+  const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
+  ProfScope prof(ctx, K_TOEP);
+  toeplitz_kernel<<<grid, kTzThreads, want, ctx->stream>>>(tm_vv, tm_gate, tm_y, p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }

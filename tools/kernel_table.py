@@ -1,0 +1,20 @@
+"""Pretty-print the per-kernel table of a bench.py JSON line (stdin or file)."""
+import json
+import sys
+
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin
+for line in src:
+    line = line.strip()
+    if not line.startswith("{"):
+        continue
+    d = json.loads(line)
+    if "kernels" not in d:
+        print(line[:300])
+        continue
+    print(f"value {d['value']:.4g} {d['unit']}  e2e {d['e2e']['value']:.4g}  tokens/s {d.get('padded_tokens_per_sec', 0):.4g}  "
+          f"ms/step {d['ms_per_step']:.2f}  launches {d['gpu_launches']}  clocks {d['clocks']}")
+    for k, v in d["kernels"].items():
+        print(f"  {k:16s} {v['ms_total']:9.2f} ms  n={v['launches']:5d}  share {v['share']:.3f}  "
+              f"{v.get('achieved', 0):9.1f} {v.get('unit', ''):8s} frac {v.get('frac', 0):.3f}")
+    if "cpu_baseline" in d:
+        print("  cpu_baseline", d["cpu_baseline"])
