@@ -314,7 +314,7 @@ static int ensure_fft_size(dcb200_ctx* ctx, dcb200_weights* w, int N) {
   return DCB200_OK;
 }
 
-// Toeplitz core-matrix tables of all layers (17 MB each), built on first use
+// Toeplitz core-matrix tables of all layers (35 MB each), built on first use
 static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w) {
   if (w->layer[0].toep) return DCB200_OK;
   for (int l = 0; l < kLayers; ++l) {

@@ -11,11 +11,12 @@
 // (n/8 = a, s'/8 = b) then depends on a + b only, so ONE array of (L/8 + 32) core matrices
 //     E[i][r][c] = k'[8 i + 7 - r - c]           (128 bytes per i, stored by descending i, zero for negative taps)
 // with LBO = SBO = 128 bytes serves every (output tile, input block) pair of the channel: the descriptor start
-// address selects Q.  E is 16 L + 4096 bytes per channel (20 KB at L = 1024) and is bulk-copied into shared memory
-// once per work item, so the kernel's global traffic is the algorithmic minimum: read vv and gate, write y.
-// Causality (s > t) falls out of the zero taps.
+// address selects Q.  A 64-token K chunk touches a window of 40 consecutive core matrices (5 KB), which the producer
+// bulk-copies from the (L2-resident, 16 L bytes per channel) table next to the 16 KB A tile of the same pipeline
+// stage, so HBM traffic stays at the algorithmic minimum: read vv and gate, write y.  Causality (s > t) falls out of
+// the zero taps.  Cost grows with L (64 KFLOP x (L/128 + 1)/2 per token); used up to L = 8192.
 //
-//   warp 0   producer: E bulk copy per item + A tiles (3-D TMA box 64 tokens x 1 channel x 128 rows)
+//   warp 0   producer: per stage one A tile (3-D TMA box 64 tokens x 1 channel x 128 rows) + its E window
 //   warp 1   MMA issuer (tcgen05.mma M=128, N=256 / 128 on the diagonal block, K=16)
 //   warp 2   TMEM allocator
 //   warp 3   gate-tile loader (TMA, same box shape)
@@ -30,7 +31,9 @@ namespace dcb {
 using namespace ptx;
 
 constexpr int kTzThreads = 384;
-constexpr int kTzAStages = 6;   // 16 KB each: 128 rows x 64 tokens
+constexpr int kTzAStages = 6;   // 16 KB A tile (128 rows x 64 tokens) + 5 KB window of Toeplitz core matrices
+constexpr uint32_t kTzWin = 40 * 128;           // bytes of one E window
+constexpr uint32_t kTzStage = 128 * 128 + 6144; // stage pitch (keeps the A tiles 1024-byte aligned)
 constexpr int kTzGSlots = 3;    // 16 KB each
 constexpr int kTzZeroChunks = 32;
 constexpr uint32_t kTzBox = 128 * 128;  // bytes of one TMA box
@@ -58,7 +61,6 @@ struct ToepParams {
   int L;                   // padded length (multiple of 128, <= kToepMaxL)
   int n_rt;                // ceil(B / 128)
   int n_items;             // 256 * n_rt
-  int nE;                  // E buffers in smem (2 when they fit, else 1)
 };
 
 __device__ __forceinline__ uint32_t tz_pack(float a, float b) {
@@ -71,19 +73,15 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmY, const ToepParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t e_bytes = (uint32_t)(p.L / 8 + kTzZeroChunks) * 128u;
   const uint32_t a_base = smem_u32(smem);
-  const uint32_t g_base = a_base + kTzAStages * kTzBox;
-  const uint32_t e_base = g_base + kTzGSlots * kTzBox;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (kTzAStages + kTzGSlots) * kTzBox + (size_t)p.nE * e_bytes);
-  // bars: afull[S] aempty[S] gfull[G] gempty[G] efull[2] eempty[2] tfull[2] tempty[2]
+  const uint32_t g_base = a_base + kTzAStages * kTzStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTzAStages * kTzStage + kTzGSlots * kTzBox);
+  // bars: afull[S] aempty[S] gfull[G] gempty[G] (4 unused) tfull[2] tempty[2]
   const uint32_t bar_base = smem_u32(bars);
   auto afull = [&](int s) { return bar_base + 8u * s; };
   auto aempty = [&](int s) { return bar_base + 8u * (kTzAStages + s); };
   auto gfull = [&](int s) { return bar_base + 8u * (2 * kTzAStages + s); };
   auto gempty = [&](int s) { return bar_base + 8u * (2 * kTzAStages + kTzGSlots + s); };
-  auto efull = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + s); };
-  auto eempty = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + 2 + s); };
   auto tfull = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + 4 + s); };
   auto tempty = [&](int s) { return bar_base + 8u * (2 * kTzAStages + 2 * kTzGSlots + 6 + s); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTzAStages + 2 * kTzGSlots + 8);
@@ -106,8 +104,6 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       mbar_init(gempty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(efull(s), 1);
-      mbar_init(eempty(s), 1);
       mbar_init(tfull(s), 1);
       mbar_init(tempty(s), 256);
     }
@@ -126,27 +122,26 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
   const int n_tiles = (L + 255) / 256;
 
   if (warp == 0) {
-    // ===== producer: E per item, A tiles =====
+    // ===== producer: A tile + E window per stage =====
     if (lane == 0) {
-      int stage = 0, eb = 0;
-      uint32_t phase = 0, ephase = 0;
-      const __nv_bfloat16* e_src0 = p.E + (size_t)((kToepMaxL - L) / 8) * 64;
+      int stage = 0;
+      uint32_t phase = 0;
+      constexpr int kP = kToepMaxL / 8 + kTzZeroChunks;  // chunks per channel in the table
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
         const int c = o / p.n_rt, rt = o % p.n_rt;
-        mbar_wait(eempty(eb), ephase ^ 1);
-        mbar_arrive_expect_tx(efull(eb), e_bytes);
-        bulk_load_1d(e_base + eb * e_bytes, e_src0 + (size_t)c * (kToepMaxL / 8 + kTzZeroChunks) * 64, e_bytes, efull(eb));
-        if (++eb == p.nE) {
-          eb = 0;
-          ephase ^= 1;
-        }
+        const __nv_bfloat16* e_ch = p.E + (size_t)c * kP * 64;
         for (int J = 0; J < n_tiles; ++J) {
           const int t_hi = min(256 * J + 255, L - 1);
           const int nkc = 2 * (t_hi / 128 + 1);  // 64-token chunks of the input blocks 0..t_hi/128
+          const int q0 = (t_hi - 7) / 8;
           for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(aempty(stage), phase ^ 1);
-            mbar_arrive_expect_tx(afull(stage), kTzBox);
-            tma_load_3d(a_base + stage * kTzBox, &tmV, afull(stage), kc * 64, c, rt * 128);
+            mbar_arrive_expect_tx(afull(stage), kTzBox + kTzWin);
+            const uint32_t dst = a_base + stage * kTzStage;
+            tma_load_3d(dst, &tmV, afull(stage), kc * 64, c, rt * 128);
+            // window: core matrices i = q, q-1, ..., q-39 (table position p = kToepMaxL/8 - 1 - i)
+            const int q = q0 - 8 * kc;
+            bulk_load_1d(dst + kTzBox, e_ch + (size_t)(kToepMaxL / 8 - 1 - q) * 64, kTzWin, afull(stage));
             if (++stage == kTzAStages) {
               stage = 0;
               phase ^= 1;
@@ -158,16 +153,13 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int stage = 0, eb = 0, acc = 0;
-      uint32_t phase = 0, ephase = 0, acc_phase = 0;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
-        mbar_wait(efull(eb), ephase);
-        const uint32_t e_addr = e_base + eb * e_bytes;
         for (int J = 0; J < n_tiles; ++J) {
           const int t_hi = min(256 * J + 255, L - 1);
           const int ntile = t_hi - 256 * J + 1;  // 256 or 128
           const int ilast = t_hi / 128;
-          const int q0 = (t_hi - 7) / 8;         // q of (i = 0, half 0, k = 0)
           mbar_wait(tempty(acc), acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 256;
@@ -178,12 +170,11 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
             for (int hh = 0; hh < 2; ++hh) {
               mbar_wait(afull(stage), phase);
               tc_fence_after();
-              const uint32_t a_addr = a_base + stage * kTzBox;
-              const int q = q0 - 16 * i - 8 * hh;
+              const uint32_t a_addr = a_base + stage * kTzStage;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t adesc = make_desc_sw128(a_addr + k * 32, 16, 1024);
-                const uint64_t bdesc = make_desc_nosw(e_addr + (uint32_t)(L / 8 - 1 - (q - 2 * k)) * 128u, 128, 128);
+                const uint64_t bdesc = make_desc_nosw(a_addr + kTzBox + k * 256, 128, 128);
                 umma_bf16(d_tmem, adesc, bdesc, idesc, (i | hh | k) ? 1u : 0u);
               }
               umma_commit(aempty(stage));
@@ -198,11 +189,6 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
             acc = 0;
             acc_phase ^= 1;
           }
-        }
-        umma_commit(eempty(eb));  // E buffer reusable once every MMA of this item has retired
-        if (++eb == p.nE) {
-          eb = 0;
-          ephase ^= 1;
         }
       }
     }
@@ -372,14 +358,11 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, const CUtensor
   p.L = L;
   p.n_rt = (B + 127) / 128;
   p.n_items = 256 * p.n_rt;
-  const size_t e_bytes = (size_t)(L / 8 + kTzZeroChunks) * 128;
-  const size_t fixed = (size_t)(kTzAStages + kTzGSlots) * kTzBox + 1024 + 512;
-  p.nE = (fixed + 2 * e_bytes <= 227 * 1024) ? 2 : 1;
-  const size_t want = fixed + p.nE * e_bytes;
-  static size_t configured = 0;
-  if (want > configured) {
+  const size_t want = (size_t)kTzAStages * kTzStage + (size_t)kTzGSlots * kTzBox + 1024 + 512;
+  static bool configured = false;
+  if (!configured) {
     DCB_CUDA(cudaFuncSetAttribute(toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-    configured = want;
+    configured = true;
   }
   const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   ProfScope prof(ctx, K_TOEP);

@@ -158,13 +158,14 @@ def test_forward_logits_and_labels(ref, gpu, B, L, conv_kind):
     assert torch.equal(lb.bool(), lg[..., 1] > lg[..., 0])
 
 
-def test_forward_long_read_uses_fft(ref, gpu):
+@pytest.mark.parametrize("B,L", [(2, 4224), (1, 8192)])
+def test_forward_long_read(ref, gpu, B, L, conv_kind):
     rng = np.random.default_rng(12)
-    ids, q = make_batch(rng, 2, 4224)        # > 4096 tokens: shared-memory FFT path
+    ids, q = make_batch(rng, B, L)
     with torch.no_grad():
         want = ref(ids, q)
     got = gpu(ids.cuda(), q.cuda()).cpu()
-    close("logits L=4224", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    close(f"logits L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
 
 
 def test_forward_arbitrary_length_is_right_filled(ref, gpu):
