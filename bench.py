@@ -31,7 +31,7 @@ METRIC = "bases_per_sec_predict_smooth"
 UNIT = "bases/s"
 
 # algorithmic work per padded token (SURVEY §8d / DESIGN.md), used for the roofline figures
-FLOPS_PER_TOKEN = {"in_proj": 2 * 256 * 768, "out_proj": 2 * 256 * 256, "fc1": 2 * 256 * 1024, "fc2": 2 * 1024 * 256,
+FLOPS_PER_TOKEN = {"mlp": 2 * 2 * 256 * 1024, "in_proj": 2 * 256 * 768, "out_proj": 2 * 256 * 256, "fc1": 2 * 256 * 1024, "fc2": 2 * 1024 * 256,
                    "head1": 2 * 256 * 1024, "head2": 2 * (1024 * 1024 + 2 * 1024)}
 BYTES_PER_TOKEN = {"hyena_conv": 768 * 2 + 256 * 2,        # FFT path: read z (3 channels) + write y, bf16
                    "shortconv_gate": 768 * 2 + 2 * 256 * 2,  # read z, write vv + gate

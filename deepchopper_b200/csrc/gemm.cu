@@ -558,6 +558,27 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
   return DCB200_OK;
 }
 
+// fp32 row-major [rows][cols]; box = 128 rows x 32 columns (128 bytes), 128B swizzle: the epilogues' residual / h tiles
+int make_tmap_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return DCB200_ECUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d f32 rows=%llu) failed: %d", (unsigned long long)rows, (int)r);
+    return DCB200_ECUDA;
+  }
+  return DCB200_OK;
+}
+
 // bf16 [B][C][L] (L contiguous); box = 64 (L) x 64 (C) x 1, 128B swizzle: an MN-major operand tile
 int make_tmap_3d_cm(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L) {
   PFN_encodeTiled enc = get_encode();

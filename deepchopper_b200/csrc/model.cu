@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "fftconv.h"
 #include "gemm.h"
+#include "mlp.h"
 #include "toeplitz.h"
 
 #include <stdlib.h>
@@ -32,6 +33,7 @@ struct LayerW {
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
   __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
   CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
+  CUtensorMap tm_w1u, tm_w2u;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
 };
 
 }  // namespace dcb
@@ -263,6 +265,8 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_fc1, lw.w_fc1, kInner, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_fc2, lw.w_fc2, kD, kInner, 256));
+    DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 64));
+    DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
   }
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.weight", kD, &w->lnf_g));
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.bias", kD, &w->lnf_b));
@@ -394,7 +398,11 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     DCB_CHECK(make_tmap_3d_rows(&tm_gate, gate, B, kD, L));
     DCB_CHECK(make_tmap_3d_rows(&tm_yr, y, B, kD, L));
   }
-  CUtensorMap tm_u, tm_y, tm_g;
+  CUtensorMap tm_u, tm_y, tm_g, tm_hA, tm_hB;
+  DCB_CHECK(make_tmap_2d_f32(&tm_hA, hA, T, kD));
+  DCB_CHECK(make_tmap_2d_f32(&tm_hB, hB, T, kD));
+  const char* mlp_env = getenv("DCB200_MLP");
+  const bool fused_mlp = !(mlp_env && !strcmp(mlp_env, "unfused"));
   DCB_CHECK(make_tmap_2d(&tm_u, u, T, kD, 128));
   DCB_CHECK(make_tmap_3d_cm(&tm_y, y, B, kD, L));
   DCB_CHECK(make_tmap_2d(&tm_g, g, T, kInner, 128));
@@ -450,21 +458,35 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     DCB_CHECK(launch_gemm(ctx, G_OUTPROJ, tm_y, lw.tm_out, p));
     DCB_STAGE_DONE();
 
-    p = gp;
-    p.bias = lw.b_fc1;
-    p.out_bf16 = g;
-    DCB_CHECK(launch_gemm(ctx, G_FC1, tm_u, lw.tm_fc1, p));
-    DCB_STAGE_DONE();
+    const float* nln_g = (l + 1 < kLayers) ? w->layer[l + 1].ln1_g : w->lnf_g;
+    const float* nln_b = (l + 1 < kLayers) ? w->layer[l + 1].ln1_b : w->lnf_b;
+    if (fused_mlp) {
+      MlpParams mp;
+      mp.num_pairs = (int)((T / 128 + 1) / 2);
+      mp.b1 = lw.b_fc1;
+      mp.b2 = lw.b_fc2;
+      mp.ln_g = nln_g;
+      mp.ln_b = nln_b;
+      DCB_CHECK(launch_mlp(ctx, tm_u, lw.tm_w1u, lw.tm_w2u, tm_hB, tm_hA, tm_u, mp));
+      DCB_STAGE_DONE();
+      DCB_STAGE_DONE();
+    } else {
+      p = gp;
+      p.bias = lw.b_fc1;
+      p.out_bf16 = g;
+      DCB_CHECK(launch_gemm(ctx, G_FC1, tm_u, lw.tm_fc1, p));
+      DCB_STAGE_DONE();
 
-    p = gp;
-    p.bias = lw.b_fc2;
-    p.resid = hB;
-    p.h_out = hA;  // (the last layer's value is not consumed again, but the epilogue stages through it)
-    p.ln_g = (l + 1 < kLayers) ? w->layer[l + 1].ln1_g : w->lnf_g;
-    p.ln_b = (l + 1 < kLayers) ? w->layer[l + 1].ln1_b : w->lnf_b;
-    p.out_bf16 = u;
-    DCB_CHECK(launch_gemm(ctx, G_FC2, tm_g, lw.tm_fc2, p));
-    DCB_STAGE_DONE();
+      p = gp;
+      p.bias = lw.b_fc2;
+      p.resid = hB;
+      p.h_out = hA;  // (the last layer's value is not consumed again, but the epilogue stages through it)
+      p.ln_g = nln_g;
+      p.ln_b = nln_b;
+      p.out_bf16 = u;
+      DCB_CHECK(launch_gemm(ctx, G_FC2, tm_g, lw.tm_fc2, p));
+      DCB_STAGE_DONE();
+    }
   }
   GemmParams p = gp;
   p.bias = w->bh1;

@@ -122,17 +122,13 @@ def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
         h1_ref = F.linear(y.transpose(1, 2), bf(lay.mixer.out_linear.weight), lay.mixer.out_linear.bias) + hA
         close("out_proj+res", hB, h1_ref, 1e-3 + 2e-3 * h1_ref.abs().mean().item(), 1e-3)
         close("ln2", m, lay.norm2(hB), 1e-2, 1e-2)
-        # stage 4: fc1 + gelu
-        run_debug(gpu, tok, qd, 4)
-        g = read_ws(gpu, "act_g", (B, L, 1024), "bf16")
-        g_ref = F.gelu(F.linear(m, bf(lay.mlp.fc1.weight), lay.mlp.fc1.bias), approximate="tanh")
-        close("fc1+gelu", g, g_ref, 5e-3, 1e-2)
-        # stage 5: fc2 + residual + next LN1
+        # stages 4-5: fused MLP (fc1 + gelu + fc2 + residual + next LN1); the hidden activation stays on chip (bf16)
         run_debug(gpu, tok, qd, 5)
         hA2 = read_ws(gpu, "act_hA", (B, L, 256), "f32")
         u2 = read_ws(gpu, "act_u", (B, L, 256), "bf16")
-        h2_ref = F.linear(g, bf(lay.mlp.fc2.weight), lay.mlp.fc2.bias) + hB
-        close("fc2+res", hA2, h2_ref, 1e-3 + 2e-3 * h2_ref.abs().mean().item(), 1e-3)
+        g_ref = bf(F.gelu(F.linear(m, bf(lay.mlp.fc1.weight), lay.mlp.fc1.bias), approximate="tanh"))
+        h2_ref = F.linear(g_ref, bf(lay.mlp.fc2.weight), lay.mlp.fc2.bias) + hB
+        close("mlp+res", hA2, h2_ref, 2e-3 + 3e-3 * h2_ref.abs().mean().item(), 1e-3)
         close("ln1_next", u2, bb.layers[1].norm1(hA2), 1e-2, 1e-2)
 
 
