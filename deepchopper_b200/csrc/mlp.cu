@@ -11,9 +11,16 @@
 // can only keep ~50 GB/s per SM in flight against L2 latency, and one CTA alone would need twice that.
 //
 //   TMEM   [0,256) acc2 (fc2 accumulator)   [256,384) [384,512) acc1 stages (fc1 chunk accumulators)
-//   smem   m tile 64 KB | weight ring 4 x 16 KB | G 2 x 32 KB (gelu chunk = A of fc2) | 2 x 16 KB staging
-//          staging slots hold TMA-loaded residual boxes that become TMA-stored h_out / u boxes in place; the G buffers
-//          double as four more slots once the tile's last fc2 MMAs have retired
+//   smem   m tile 64 KB | weight ring 6 x 16 KB | G 32 KB (gelu chunk = A of fc2) | 2 x 16 KB staging
+//          The ring must cover the L2 round trip (~1 us) of the weight stream: three MMA groups in flight.  G is single-
+//          buffered: GELU(j+1) is computed in registers while fc2(j) still reads G and written once fc2(j) retires,
+//          which hides behind fc2(j) + fc1(j+2) on the tensor pipe.  Staging slots hold the h_out / u boxes on their way
+//          to TMA stores; G doubles as two more slots once the tile's last fc2 has retired.  The fp32 residual never
+//          waits on the critical path: its eight 32-column boxes stream through D0/D1 by TMA DURING the chunk loop and
+//          are added straight into the fc2 accumulator in TMEM by two of the epilogue warp groups, in the window
+//          between fc2(j-1) retiring and G(j) being published (the tensor pipe runs fc1(j+1) meanwhile).
+//          Bias / LayerNorm vectors live in the kernel parameters (constant bank, warp-uniform reads): with 227 KB of
+//          shared memory carved out there is no L1 left for __ldg.
 //   warp 0  weight-ring producer (both CTAs; completion bytes are credited to the leader's barrier)
 //   warp 1  MMA issuer (leader CTA only): fc1(0) fc1(1) | fc2(j) fc1(j+2) ...  fc1 of the next chunk is queued before
 //           fc2 so the tensor pipe stays busy while the epilogue warps GELU the current chunk
@@ -35,10 +42,10 @@ using namespace ptx;
 namespace {
 
 constexpr int kThreads = 640;  // 4 service warps + 16 epilogue warps
-constexpr int kSlots = 4;
+constexpr int kSlots = 6;
 constexpr uint32_t kUnitBytes = 128 * 128;  // 128 rows x 64 bf16 (or 2 x 64 rows x 64 bf16)
 constexpr uint32_t kABytes = 4 * kUnitBytes;
-constexpr uint32_t kGBytes = 2 * kUnitBytes;
+constexpr uint32_t kGBytes = 2 * kUnitBytes;  // one gelu chunk: 128 rows x 128 k
 constexpr int kChunks = 8;                  // 1024 hidden / 128
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -60,6 +67,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// Optional timeline trace (DCB200_TRACE=1): (tag, SM clock) records of one MMA thread / one epilogue warp / one producer,
+// read back with dcb200_ctx_read_workspace("trace").  Costs one predictable branch when off.
+constexpr int kTraceCap = 4096;
+struct Tracer {
+  long long* buf;
+  int n;
+  __device__ __forceinline__ void operator()(int tag) {
+    if (buf && n < kTraceCap) {
+      buf[2 * n] = tag;
+      buf[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -73,9 +95,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
   if (smem_u32(smem) & 1023u) __trap();
   const uint32_t a_base = smem_u32(smem);
   const uint32_t w_base = a_base + kABytes;
-  const uint32_t g_base = w_base + kSlots * kUnitBytes;  // G[0] = slots 0,1 ; G[1] = slots 2,3
-  const uint32_t r_base = g_base + 2 * kGBytes;          // dedicated staging slots D[0], D[1] (one per column half)
-  uint8_t* tail = smem + kABytes + kSlots * kUnitBytes + 2 * kGBytes + 2 * kUnitBytes;
+  const uint32_t g_base = w_base + kSlots * kUnitBytes;  // G (also staging slots s0, s1 at the end of a tile)
+  const uint32_t r_base = g_base + kGBytes;              // dedicated staging slots D0, D1
+  uint8_t* tail = smem + kABytes + kSlots * kUnitBytes + kGBytes + 2 * kUnitBytes;
   float2* stats = reinterpret_cast<float2*>(tail);  // [2 part pairs][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * 128 * 8);
   const uint32_t bar_base = smem_u32(bars);
@@ -83,8 +105,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
   // TMA loads signal it through its shared::cluster address), "B" = both copies, signalled by multicast commits.
   enum { A_FULL = 0 /*L*/, A_EMPTY = 1 /*B*/, W_FULL = 2 /*L*/, W_EMPTY = W_FULL + kSlots /*B*/,
          T1_FULL = W_EMPTY + kSlots /*B*/, T1_EMPTY = T1_FULL + 2 /*L*/, G_FULL = T1_EMPTY + 2 /*L*/,
-         G_EMPTY = G_FULL + 2 /*B*/, T2_FULL = G_EMPTY + 2 /*B*/, T2_EMPTY = T2_FULL + 1 /*L*/,
-         R_FULL = T2_EMPTY + 1 /*local: s0..s3, D0a, D1a, D0b, D1b*/, GD0 = R_FULL + 8 /*B*/, N_BARS = GD0 + 1 };
+         G_EMPTY = G_FULL + 1 /*B*/, T2_FULL = G_EMPTY + 1 /*B*/, T2_EMPTY = T2_FULL + 1 /*L*/, R_FULL = T2_EMPTY + 1 /*local: D0, D1*/,
+         N_BARS = R_FULL + 2 };
   auto bar = [&](int i) { return bar_base + 8u * i; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
@@ -99,8 +121,6 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
     prefetch_tmap(&tmW1);
     prefetch_tmap(&tmW2);
     prefetch_tmap(&tmHin);
-    prefetch_tmap(&tmHout);
-    prefetch_tmap(&tmU);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar(A_FULL), 1);
@@ -112,13 +132,12 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(T1_FULL + s), 1);
       mbar_init(bar(T1_EMPTY + s), 32);  // one arrival per epilogue warp of both CTAs
-      mbar_init(bar(G_FULL + s), 32);
-      mbar_init(bar(G_EMPTY + s), 1);
     }
+    mbar_init(bar(G_FULL), 32);
+    mbar_init(bar(G_EMPTY), 1);
     mbar_init(bar(T2_FULL), 1);
     mbar_init(bar(T2_EMPTY), 32);
-    for (int s = 0; s < 8; ++s) mbar_init(bar(R_FULL + s), 1);
-    mbar_init(bar(GD0), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(bar(R_FULL + s), 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -131,6 +150,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int num_pairs = p.num_pairs;
+  const bool traced = p.trace != nullptr && blockIdx.x == 0;
   const int pair0 = (int)cluster_id_x(), pair_step = (int)cluster_nclusters_x();
 
   if (warp == 0) {
@@ -138,6 +158,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
+      Tracer tr{traced ? p.trace + 2 * 2 * kTraceCap : nullptr, 0};
       uint32_t wfull[kSlots];
       for (int s = 0; s < kSlots; ++s) wfull[s] = lbar(W_FULL + s);
       auto advance = [&]() {
@@ -149,7 +170,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       // fc1 chunk j: my 64 rows (hidden units) of W1 x K = 256 -> two slots, each [kb even 8 KB][kb odd 8 KB]
       auto load_fc1 = [&](int j) {
         for (int h = 0; h < 2; ++h) {
+          tr(300 + j);
           mbar_wait(bar(W_EMPTY + slot), phase ^ 1);
+          tr(310 + j);
           if (leader) mbar_arrive_expect_tx(bar(W_FULL + slot), 2 * kUnitBytes);
           const uint32_t dst = w_base + slot * kUnitBytes;
           tma_load_2d_2sm(dst, &tmW1, wfull[slot], (2 * h) * 64, j * 128 + (int)rank * 64);
@@ -160,7 +183,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       // fc2 chunk j: my 128 rows (output features) of W2 x K = 128 -> two slots of 64 k
       auto load_fc2 = [&](int j) {
         for (int kb = 0; kb < 2; ++kb) {
+          tr(320 + j);
           mbar_wait(bar(W_EMPTY + slot), phase ^ 1);
+          tr(330 + j);
           if (leader) mbar_arrive_expect_tx(bar(W_FULL + slot), 2 * kUnitBytes);
           tma_load_2d_2sm(w_base + slot * kUnitBytes, &tmW2, wfull[slot], j * 128 + kb * 64, (int)rank * 128);
           advance();
@@ -183,6 +208,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       int slot = 0;
       uint32_t wphase = 0;
       uint32_t n = 0;  // tile pairs done by this cluster
+      Tracer tr{traced ? p.trace : nullptr, 0};
       auto advance = [&]() {
         if (++slot == kSlots) {
           slot = 0;
@@ -194,11 +220,14 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
         auto fc1 = [&](int j) {
           const int s = j & 1;
           const uint32_t use = 4 * n + (j >> 1);
+          tr(100 + j);
           mbar_wait_cluster(bar(T1_EMPTY + s), (use & 1) ^ 1);
+          tr(110 + j);
           tc_fence_after();
           const uint32_t d = tmem_base + 256 + 128 * s;
           for (int h = 0; h < 2; ++h) {
             mbar_wait(bar(W_FULL + slot), wphase);
+            tr(120 + j);
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
@@ -215,15 +244,17 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
           if (j == kChunks - 1) umma_commit_2sm(bar(A_EMPTY), 3);
         };
         auto fc2 = [&](int j) {
-          const int s = j & 1;
-          const uint32_t use = 4 * n + (j >> 1);
-          mbar_wait_cluster(bar(G_FULL + s), use & 1);
+          tr(200 + j);
+          mbar_wait_cluster(bar(G_FULL), j & 1);  // (8 uses per tile: parity of 8 n + j)
+          tr(210 + j);
           if (j == 0) mbar_wait_cluster(bar(T2_EMPTY), (n & 1) ^ 1);
+          tr(220 + j);
           tc_fence_after();
           for (int kb = 0; kb < 2; ++kb) {
             mbar_wait(bar(W_FULL + slot), wphase);
+            tr(230 + j);
             tc_fence_after();
-            const uint32_t a_addr = g_base + s * kGBytes + kb * kUnitBytes;
+            const uint32_t a_addr = g_base + kb * kUnitBytes;
             const uint32_t b_addr = w_base + slot * kUnitBytes;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -232,11 +263,12 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
             umma_commit_2sm(bar(W_EMPTY + slot), 3);
             advance();
           }
-          umma_commit_2sm(bar(G_EMPTY + s), 3);
-          if (j == kChunks - 2) umma_commit_2sm(bar(GD0), 3);  // G[0] is dead for the rest of the tile
+          umma_commit_2sm(bar(G_EMPTY), 3);
           if (j == kChunks - 1) umma_commit_2sm(bar(T2_FULL), 3);
         };
+        tr(90);
         mbar_wait(bar(A_FULL), n & 1);
+        tr(91);
         tc_fence_after();
         fc1(0);
         fc1(1);
@@ -247,29 +279,22 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       }
     }
   } else if (warp == 3) {
-    // ===== m-tile loader + early residual loads =====
+    // ===== m-tile loader (one tile ahead) + L2 prefetch of the tile's residual =====
     if (lane == 0) {
-      uint32_t n = 0;
       const uint32_t afull = lbar(A_FULL);
-      for (int pr = pair0; pr < num_pairs; pr += pair_step, ++n) {
+      auto load_m = [&](int pr) {
         const int tok0 = pr * 256 + (int)rank * 128;
-        mbar_wait(bar(A_EMPTY), (n & 1) ^ 1);
         if (leader) mbar_arrive_expect_tx(bar(A_FULL), 2 * kABytes);
         for (int kb = 0; kb < 4; ++kb) tma_load_2d_2sm(a_base + kb * kUnitBytes, &tmM, afull, kb * 64, tok0);
-        // pull this tile's residual (128 rows x 1 KB) into L2 now; the staged TMA loads below then hit L2
         for (int kb = 0; kb < 8; ++kb) tma_prefetch_2d(&tmHin, kb * 32, tok0);
-        // Residual boxes staged through the G buffers once they are dead (see the epilogue's staging table);
-        // (once-per-tile barriers: a parity wait cannot tell completions two apart, so G_EMPTY cannot be used here)
-        mbar_wait(bar(GD0), n & 1);
-        for (int h = 0; h < 2; ++h) {  // s0 <- box 4, s1 <- box 6 (step 0 of parts 2,3)
-          mbar_arrive_expect_tx(bar(R_FULL + h), kUnitBytes);
-          tma_load_2d(g_base + h * kUnitBytes, &tmHin, bar(R_FULL + h), (2 + h) * 64, tok0);
-        }
-        mbar_wait(bar(T2_FULL), n & 1);
-        for (int h = 0; h < 2; ++h) {  // s2 <- box 1, s3 <- box 3 (step 1 of parts 0,1)
-          mbar_arrive_expect_tx(bar(R_FULL + 2 + h), kUnitBytes);
-          tma_load_2d(g_base + (2 + h) * kUnitBytes, &tmHin, bar(R_FULL + 2 + h), h * 64 + 32, tok0);
-        }
+        if (pr + pair_step < num_pairs)  // the tile after this one: its m load (issued late, at fc1(7)) will then hit L2
+          for (int kb = 0; kb < 4; ++kb) tma_prefetch_2d(&tmM, kb * 64, tok0 + pair_step * 256);
+      };
+      if (pair0 < num_pairs) load_m(pair0);
+      uint32_t n = 0;
+      for (int pr = pair0; pr + pair_step < num_pairs; pr += pair_step, ++n) {
+        mbar_wait(bar(A_EMPTY), n & 1);  // fc1(7) of tile n has retired: the m buffer is free for tile n+1
+        load_m(pr + pair_step);
       }
     }
   } else if (warp >= 4) {
@@ -281,49 +306,48 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const bool storer = (lane == 0 && quad == 0);  // one per part
     const uint32_t t1_empty[2] = {lbar(T1_EMPTY), lbar(T1_EMPTY + 1)};
-    const uint32_t g_full[2] = {lbar(G_FULL), lbar(G_FULL + 1)};
+    const uint32_t g_full = lbar(G_FULL);
     const uint32_t t2_empty = lbar(T2_EMPTY);
     uint32_t n = 0;
     uint32_t v[32];
+    Tracer tr{(traced && warp == 4 && lane == 0) ? p.trace + 2 * kTraceCap : nullptr, 0};
     const uint64_t kC0 = f2_pack(0.7978845608f, 0.7978845608f), kC1 = f2_pack(0.0356774081f, 0.0356774081f);
     const uint64_t kHalf = f2_pack(0.5f, 0.5f);
-    // Staging of the final epilogue.  Part p owns the 32-column fp32 boxes 2p (step 0) and 2p+1 (step 1):
-    //   step 0:  p=0 D0a   p=1 D1a   p=2 s0   p=3 s1        (D* dedicated, s0,s1 = G[0], s2,s3 = G[1])
-    //   step 1:  p=0 s2    p=1 s3    p=2 D0b  p=3 D1b       (D0b/D1b: refilled by the storers of parts 0/1 after step 0)
-    // R_FULL indices: s0..s3 = 0..3, D0a,D1a = 4,5, D0b,D1b = 6,7 -- every one completes exactly once per tile.
-    const uint32_t slot_addr[2] = {
-        part < 2 ? r_base + part * kUnitBytes : g_base + (part - 2) * kUnitBytes,
-        part < 2 ? g_base + (2 + part) * kUnitBytes : r_base + (part - 2) * kUnitBytes};
-    const int slot_bar[2] = {part < 2 ? 4 + part : part - 2, part < 2 ? 2 + part : 6 + (part - 2)};
-    if (storer && part < 2 && pair0 < num_pairs) {  // first tile: residual box 2*part -> D[part]
-      mbar_arrive_expect_tx(bar(R_FULL + 4 + part), kUnitBytes);
-      tma_load_2d(r_base + part * kUnitBytes, &tmHin, bar(R_FULL + 4 + part), part * 64, pair0 * 256 + (int)rank * 128);
-    }
+    // Final-epilogue staging: part p owns the columns [64p, 64p+64) and ONE 16 KB slot (parts 0,1 the dedicated D0,D1,
+    // parts 2,3 the halves of G, dead once the tile's last fc2 has retired) through which its two fp32 h_out boxes and
+    // its bf16 u box go to TMA stores.
+    const uint32_t my_slot = part < 2 ? r_base + part * kUnitBytes : g_base + (part - 2) * kUnitBytes;
+    // Residual injection (parts 0,1 only): part p adds the boxes p, p+2, p+4, p+6 (32 fp32 columns each) through D[p].
+    const uint32_t my_rfull = bar(R_FULL + (part & 1));
+    uint32_t rphase = 0;
     for (int pr = pair0; pr < num_pairs; pr += pair_step, ++n) {
       const int tok0 = pr * 256 + (int)rank * 128;
+      if (storer && part < 2) {  // first residual box of the tile -> D[part] (free since the end-of-tile barrier)
+        mbar_arrive_expect_tx(my_rfull, kUnitBytes);
+        tma_load_2d(my_slot, &tmHin, my_rfull, part * 32, tok0);
+      }
       // ---- GELU chunks: acc1[s] -> bf16 K-major tile G[s]; my 32 of the chunk's 128 columns ---------------------
       for (int j = 0; j < kChunks; ++j) {
         const int s = j & 1;
         const uint32_t use = 4 * n + (j >> 1);
+        tr(400 + j);
         mbar_wait(bar(T1_FULL + s), use & 1);
+        tr(410 + j);
         tc_fence_after();
         tmem_ld32(tmem_base + lane_off + 256 + 128 * s + part * 32, v);
-        const float* b1 = p.b1 + j * 128 + part * 32;
-        float4 bias[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bias[q] = __ldg(reinterpret_cast<const float4*>(b1 + q * 4));
+        const float* b1 = p.b1 + j * 128 + part * 32;  // kernel-parameter (constant bank) array, warp-uniform index
         tmem_ld_wait();
         // the accumulator stage is free as soon as it sits in registers: fc1 of chunk j+2 may start
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(t1_empty[s]);
-        mbar_wait(bar(G_EMPTY + s), (use & 1) ^ 1);  // fc2 of the previous chunk on this buffer has retired
-        const uint32_t grow = g_base + s * kGBytes + (part >> 1) * kUnitBytes + row * 128;
+        const uint32_t grow = g_base + (part >> 1) * kUnitBytes + row * 128;
+        uint32_t o[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float bj[8] = {bias[2 * q].x, bias[2 * q].y, bias[2 * q].z, bias[2 * q].w,
-                               bias[2 * q + 1].x, bias[2 * q + 1].y, bias[2 * q + 1].z, bias[2 * q + 1].w};
-          uint32_t o[4];
+          float bj[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bj[i] = b1[q * 8 + i];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             // gelu_tanh on a pair: 0.5 x (1 + tanh(x (c0 + c1 x^2))), packed fp32x2 arithmetic
@@ -337,57 +361,91 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
             const uint64_t hx = f2_mul(x, kHalf);
             float y0, y1;
             f2_unpack(f2_fma(hx, f2_pack(t0, t1), hx), y0, y1);
-            o[i] = pack_bf16(y0, y1);
+            o[q * 4 + i] = pack_bf16(y0, y1);
           }
-          sts128(grow + (((uint32_t)((part & 1) * 4 + q) ^ sw) << 4), o[0], o[1], o[2], o[3]);
         }
+        tr(420 + j);
+        mbar_wait(bar(G_EMPTY), (j & 1) ^ 1);  // fc2 of the previous chunk has finished reading G (parity of 8 n + j - 1)
+        tr(430 + j);
+        if (part < 2 && j >= 1 && j <= 4) {
+          // acc2 is quiescent (fc2(j-1) retired, fc2(j) waits for my G_FULL arrival): acc2[:, box] += residual box
+          const int col0 = (2 * (j - 1) + part) * 32;
+          uint32_t a[32];
+          mbar_wait(my_rfull, rphase);
+          rphase ^= 1;
+          tmem_ld32(tmem_base + lane_off + col0, a);
+          tmem_ld_wait();
+          const uint32_t rrow = my_slot + row * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t r[4];
+            lds128(rrow + (((uint32_t)q ^ sw) << 4), r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[4 * q + i] = __float_as_uint(__uint_as_float(a[4 * q + i]) + __uint_as_float(r[i]));
+          }
+          tmem_st32(tmem_base + lane_off + col0, a);
+          tmem_st_wait();
+          tc_fence_before();
+          if (j < 4) {  // refill D[part] with my next box
+            bar_sync(2 + part, 128);
+            if (storer) {
+              mbar_arrive_expect_tx(my_rfull, kUnitBytes);
+              tma_load_2d(my_slot, &tmHin, my_rfull, col0 + 64, tok0);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(grow + (((uint32_t)((part & 1) * 4 + q) ^ sw) << 4), o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(g_full[s]);
+        if (lane == 0) mbar_arrive_remote(g_full);
+        tr(440 + j);
       }
-      // ---- final: x = acc2 + b2 + h_in -> h_out ; LayerNorm -> u ----------------------------------------------------
+      // ---- final: x = acc2 + b2 (+ residual, already in acc2) -> h_out ; LayerNorm -> u ------------------------------
+      // Global stores are plain coalesced st.global: each warp transposes its own 32 rows through a private 4 KB
+      // scratch (row-owner writes, 4 rows x 128 B reads), so the tile's tail never waits on the TMA queue.
+      tr(500);
       mbar_wait(bar(T2_FULL), n & 1);
+      tr(501);
       tc_fence_after();
       float sum = 0.f, sq = 0.f;
-#pragma unroll 1
+      const uint32_t scratch = my_slot + quad * 4096;
+      const uint32_t own = scratch + lane * 128;                       // my row, row-owner layout
+      const int trow = lane >> 3, tchunk = lane & 7;                     // T layout: row 4 i + trow, 16-byte chunk tchunk
+      const size_t grow0 = (size_t)tok0 + quad * 32;
+#pragma unroll
       for (int st = 0; st < 2; ++st) {
         const int col0 = part * 64 + st * 32;
-        const uint32_t sbase = slot_addr[st];
-        mbar_wait(bar(R_FULL + slot_bar[st]), n & 1);
         tmem_ld32(tmem_base + lane_off + col0, v);
         tmem_ld_wait();
-        const uint32_t rrow = sbase + row * 128;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const uint32_t addr = rrow + (((uint32_t)q ^ sw) << 4);
-          uint32_t r[4];
-          lds128(addr, r);
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + q * 4));
-          const float x0 = __uint_as_float(v[4 * q]) + bb.x + __uint_as_float(r[0]);
-          const float x1 = __uint_as_float(v[4 * q + 1]) + bb.y + __uint_as_float(r[1]);
-          const float x2 = __uint_as_float(v[4 * q + 2]) + bb.z + __uint_as_float(r[2]);
-          const float x3 = __uint_as_float(v[4 * q + 3]) + bb.w + __uint_as_float(r[3]);
+          const float x0 = __uint_as_float(v[4 * q]) + p.b2[col0 + 4 * q];
+          const float x1 = __uint_as_float(v[4 * q + 1]) + p.b2[col0 + 4 * q + 1];
+          const float x2 = __uint_as_float(v[4 * q + 2]) + p.b2[col0 + 4 * q + 2];
+          const float x3 = __uint_as_float(v[4 * q + 3]) + p.b2[col0 + 4 * q + 3];
           sum += (x0 + x1) + (x2 + x3);
           sq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq))));
           v[4 * q] = __float_as_uint(x0);
           v[4 * q + 1] = __float_as_uint(x1);
           v[4 * q + 2] = __float_as_uint(x2);
           v[4 * q + 3] = __float_as_uint(x3);
-          sts128(addr, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          sts128(own + (((uint32_t)q ^ sw) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         tmem_st32(tmem_base + lane_off + col0, v);  // x stays in TMEM for the normalisation pass
-        fence_proxy_async();
-        bar_sync(2 + part, 128);
-        if (storer) {
-          tma_store_2d(&tmHout, sbase, col0, tok0);
-          bulk_commit();
-          if (st == 0 && part < 2) {  // refill D[part] with the step-1 box of part + 2
-            bulk_wait_read<0>();
-            mbar_arrive_expect_tx(bar(R_FULL + 6 + part), kUnitBytes);
-            tma_load_2d(sbase, &tmHin, bar(R_FULL + 6 + part), (part + 2) * 64 + 32, tok0);
-          }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + trow;
+          uint32_t w[4];
+          lds128(scratch + r * 128 + (((uint32_t)tchunk ^ (uint32_t)(r & 7)) << 4), w);
+          if (grow0 + r < (size_t)p.T)
+            *reinterpret_cast<uint4*>(p.h_out + (grow0 + r) * 256 + col0 + tchunk * 4) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        __syncwarp();
       }
+      tr(540);
       // row statistics (sum, sum of squares) over the four column parts, in a fixed order: (p0 + p1) + (p2 + p3)
       float2* st2 = stats + (part >> 1) * 128 + row;
       if (part & 1) *st2 = make_float2(sum, sq);
@@ -397,8 +455,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
         const float2 o = *st2;
         *st2 = make_float2(sum + o.x, sq + o.y);
       }
-      if (storer) bulk_wait_read<0>();
-      bar_sync(1, 512);  // pair sums visible; every h_out store has finished reading its slot
+      bar_sync(6 + quad, 128);
+      tr(551);
       float2 sa = stats[row];
       {
         const float2 sb = stats[128 + row];
@@ -407,10 +465,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       }
       const float mean = sa.x * (1.0f / 256.0f);
       const float rstd = rsqrtf(fmaxf(sa.y * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
-      {  // u box `part`: 64 bf16 columns x 128 rows, staged in G slot `part`
+      {  // u: my 64 bf16 columns (128 B per row)
         const int col0 = part * 64;
-        const uint32_t ubase = g_base + part * kUnitBytes;
-        const uint32_t urow = ubase + row * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           tmem_ld32(tmem_base + lane_off + col0 + c * 32, v);
@@ -418,38 +474,28 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = col0 + c * 32 + q * 8;
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_g + col));
-            const float4 gb = __ldg(reinterpret_cast<const float4*>(p.ln_g + col + 4));
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.ln_b + col));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
-            const float gj[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-            const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
             float y[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(v[q * 8 + i]) - mean) * rstd, gj[i], bj[i]);
-            sts128(urow + (((uint32_t)(c * 4 + q) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
+            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(v[q * 8 + i]) - mean) * rstd, p.ln_g[col + i], p.ln_b[col + i]);
+            sts128(own + (((uint32_t)(c * 4 + q) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
                    pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(t2_empty);  // acc2 fully drained: fc2(0) of the next tile may overwrite it
-        fence_proxy_async();
-        bar_sync(2 + part, 128);
-        if (storer) {
-          tma_store_2d(&tmU, ubase, col0, tok0);
-          bulk_commit();
-          bulk_wait_read<0>();
-          if (part < 2 && pr + pair_step < num_pairs) {  // next tile: residual box 2*part -> D[part]
-            mbar_arrive_expect_tx(bar(R_FULL + 4 + part), kUnitBytes);
-            tma_load_2d(r_base + part * kUnitBytes, &tmHin, bar(R_FULL + 4 + part), part * 64,
-                        (pr + pair_step) * 256 + (int)rank * 128);
-          }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + trow;
+          uint32_t w[4];
+          lds128(scratch + r * 128 + (((uint32_t)tchunk ^ (uint32_t)(r & 7)) << 4), w);
+          if (grow0 + r < (size_t)p.T)
+            *reinterpret_cast<uint4*>(p.u_out + (grow0 + r) * 256 + col0 + tchunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-      bar_sync(1, 512);  // all stores have finished reading the G buffers: the next tile's GELU may overwrite them
+      tr(560);
+      bar_sync(1, 512);  // every warp is done with its scratch (G halves / D slots): the next tile may reuse them
     }
-    if (storer) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -463,7 +509,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
 
 int launch_mlp(dcb200_ctx* ctx, const CUtensorMap& tm_m, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                const CUtensorMap& tm_hin, const CUtensorMap& tm_hout, const CUtensorMap& tm_u, const MlpParams& p) {
-  const size_t smem = kABytes + kSlots * kUnitBytes + 2 * kGBytes + 2 * kUnitBytes + 2 * 128 * 8 + 40 * 8;
+  const size_t smem = kABytes + kSlots * kUnitBytes + kGBytes + 2 * kUnitBytes + 2 * 128 * 8 + 40 * 8;
   static bool configured = false;
   if (!configured) {
     DCB_CUDA(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -33,6 +33,7 @@ struct LayerW {
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
   __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
   CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
+  std::vector<float> hb_fc1, hb_fc2, h_ln1_g, h_ln1_b;  // host copies: passed to kernels as constant-bank parameters
   CUtensorMap tm_w1u, tm_w2u;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
 };
 
@@ -44,6 +45,7 @@ struct dcb200_weights {
   float* emb = nullptr;  // [16][256]
   dcb::LayerW layer[dcb::kLayers];
   float *lnf_g = nullptr, *lnf_b = nullptr;
+  std::vector<float> h_lnf_g, h_lnf_b;
   __nv_bfloat16 *wh1 = nullptr, *wh2 = nullptr;
   float *bh1 = nullptr, *bh2 = nullptr, *w3 = nullptr, *b3 = nullptr;
   CUtensorMap tm_h1, tm_h2;
@@ -187,6 +189,16 @@ static int upload_f32(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd, c
   return DCB200_OK;
 }
 
+static int host_copy(const StateDict& sd, const std::string& key, int64_t numel, std::vector<float>& out) {
+  const int i = sd.find(key);
+  if (i < 0 || sd.numel[i] != numel) {
+    set_error("state dict has no tensor ending in '%s' with %lld elements", key.c_str(), (long long)numel);
+    return DCB200_EWEIGHT;
+  }
+  out.assign(sd.data[i], sd.data[i] + numel);
+  return DCB200_OK;
+}
+
 static int upload_bf16(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd, const std::string& key, int64_t numel,
                        __nv_bfloat16** out) {
   float* tmp = nullptr;
@@ -236,6 +248,10 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mlp.fc1.bias", kInner, &lw.b_fc1));
     DCB_CHECK(upload_bf16(ctx, w, sd, p + "mlp.fc2.weight", kD * kInner, &lw.w_fc2));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mlp.fc2.bias", kD, &lw.b_fc2));
+    DCB_CHECK(host_copy(sd, p + "mlp.fc1.bias", kInner, lw.hb_fc1));
+    DCB_CHECK(host_copy(sd, p + "mlp.fc2.bias", kD, lw.hb_fc2));
+    DCB_CHECK(host_copy(sd, p + "norm1.weight", kD, lw.h_ln1_g));
+    DCB_CHECK(host_copy(sd, p + "norm1.bias", kD, lw.h_ln1_b));
     // implicit filter, evaluated once for the whole positional table
     FilterW fw;
     float *z, *t, *w0, *b0, *f1, *w2, *b2, *f3, *w4, *b4, *f5, *w6, *dl;
@@ -270,6 +286,8 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
   }
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.weight", kD, &w->lnf_g));
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.bias", kD, &w->lnf_b));
+  DCB_CHECK(host_copy(sd, "ln_f.weight", kD, w->h_lnf_g));
+  DCB_CHECK(host_copy(sd, "ln_f.bias", kD, w->h_lnf_b));
   DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear1.weight", kInner * kD, &w->wh1));
   DCB_CHECK(upload_f32(ctx, w, sd, "head.linear1.bias", kInner, &w->bh1));
   DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear2.weight", kInner * kInner, &w->wh2));
@@ -461,12 +479,23 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     const float* nln_g = (l + 1 < kLayers) ? w->layer[l + 1].ln1_g : w->lnf_g;
     const float* nln_b = (l + 1 < kLayers) ? w->layer[l + 1].ln1_b : w->lnf_b;
     if (fused_mlp) {
-      MlpParams mp;
+      static thread_local MlpParams mp;  // 7 KB: keep it off the stack
       mp.num_pairs = (int)((T / 128 + 1) / 2);
-      mp.b1 = lw.b_fc1;
-      mp.b2 = lw.b_fc2;
-      mp.ln_g = nln_g;
-      mp.ln_b = nln_b;
+      mp.T = (int)T;
+      mp.h_in = hB;
+      mp.h_out = hA;
+      mp.u_out = u;
+      memcpy(mp.b1, lw.hb_fc1.data(), sizeof(mp.b1));
+      memcpy(mp.b2, lw.hb_fc2.data(), sizeof(mp.b2));
+      memcpy(mp.ln_g, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_g.data() : w->h_lnf_g.data(), sizeof(mp.ln_g));
+      memcpy(mp.ln_b, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_b.data() : w->h_lnf_b.data(), sizeof(mp.ln_b));
+      mp.trace = nullptr;
+      if (l == 0 && getenv("DCB200_TRACE")) {
+        DevBuf& bt = ctx->buf("trace");
+        DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
+        DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
+        mp.trace = bt.as<long long>();
+      }
       DCB_CHECK(launch_mlp(ctx, tm_u, lw.tm_w1u, lw.tm_w2u, tm_hB, tm_hA, tm_u, mp));
       DCB_STAGE_DONE();
       DCB_STAGE_DONE();
