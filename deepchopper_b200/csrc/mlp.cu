@@ -10,7 +10,7 @@
 // stream through shared memory once per token tile, so halving the per-SM weight bytes is what matters: a 96 KB ring
 // can only keep ~50 GB/s per SM in flight against L2 latency, and one CTA alone would need twice that.
 //
-//   TMEM   [0,256) acc2 (fc2 accumulator)   [256,384) [384,512) acc1 stages (fc1 chunk accumulators)
+//   TMEM   [0,256) acc2 (fc2 accumulator)   [256,512) acc1 (fc1 accumulator of one 256-wide hidden group)
 //   smem   m tile 64 KB | weight ring 6 x 16 KB | G 32 KB (gelu chunk = A of fc2) | 2 x 16 KB staging
 //          The ring must cover the L2 round trip (~1 us) of the weight stream: three MMA groups in flight.  G is single-
 //          buffered: GELU(j+1) is computed in registers while fc2(j) still reads G and written once fc2(j) retires,
@@ -22,8 +22,8 @@
 //          Bias / LayerNorm vectors live in the kernel parameters (constant bank, warp-uniform reads): with 227 KB of
 //          shared memory carved out there is no L1 left for __ldg.
 //   warp 0  weight-ring producer (both CTAs; completion bytes are credited to the leader's barrier)
-//   warp 1  MMA issuer (leader CTA only): fc1(0) fc1(1) | fc2(j) fc1(j+2) ...  fc1 of the next chunk is queued before
-//           fc2 so the tensor pipe stays busy while the epilogue warps GELU the current chunk
+//   warp 1  MMA issuer (leader CTA only): fc1(0) | fc2(2P) fc1(P+1) fc2(2P+1) ...  all MMAs are M = 256, N = 256; the
+//           hidden activation is consumed in 128-wide chunks j (K = 128 of fc2) through the single G buffer
 //   warp 2  TMEM allocator
 //   warp 3  m-tile loader + early residual loads (as soon as the G buffers of a tile are dead)
 //   warps 4-19 epilogue: thread = accumulator row, four warps per TMEM lane quadrant split the columns (the GELU of
@@ -104,7 +104,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
   // Barriers.  "L" = only the leader's copy is used (waited on by the leader's MMA thread; the peer's threads and
   // TMA loads signal it through its shared::cluster address), "B" = both copies, signalled by multicast commits.
   enum { A_FULL = 0 /*L*/, A_EMPTY = 1 /*B*/, W_FULL = 2 /*L*/, W_EMPTY = W_FULL + kSlots /*B*/,
-         T1_FULL = W_EMPTY + kSlots /*B*/, T1_EMPTY = T1_FULL + 2 /*L*/, G_FULL = T1_EMPTY + 2 /*L*/,
+         T1_FULL = W_EMPTY + kSlots /*B*/, T1_EMPTY = T1_FULL + 1 /*L*/, G_FULL = T1_EMPTY + 1 /*L*/,
          G_EMPTY = G_FULL + 1 /*B*/, T2_FULL = G_EMPTY + 1 /*B*/, T2_EMPTY = T2_FULL + 1 /*L*/, R_FULL = T2_EMPTY + 1 /*local: D0, D1*/,
          N_BARS = R_FULL + 2 };
   auto bar = [&](int i) { return bar_base + 8u * i; };
@@ -129,10 +129,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       mbar_init(bar(W_FULL + s), 1);
       mbar_init(bar(W_EMPTY + s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(T1_FULL + s), 1);
-      mbar_init(bar(T1_EMPTY + s), 32);  // one arrival per epilogue warp of both CTAs
-    }
+    mbar_init(bar(T1_FULL), 1);
+    mbar_init(bar(T1_EMPTY), 32);  // one arrival per epilogue warp of both CTAs
     mbar_init(bar(G_FULL), 32);
     mbar_init(bar(G_EMPTY), 1);
     mbar_init(bar(T2_FULL), 1);
@@ -167,16 +165,14 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
           phase ^= 1;
         }
       };
-      // fc1 chunk j: my 64 rows (hidden units) of W1 x K = 256 -> two slots, each [kb even 8 KB][kb odd 8 KB]
-      auto load_fc1 = [&](int j) {
-        for (int h = 0; h < 2; ++h) {
-          tr(300 + j);
+      // fc1 group P (256 hidden units): my 128 rows of W1 x K = 256 -> four slots of 64 k
+      auto load_fc1 = [&](int P) {
+        for (int kb = 0; kb < 4; ++kb) {
+          tr(300 + P);
           mbar_wait(bar(W_EMPTY + slot), phase ^ 1);
-          tr(310 + j);
+          tr(310 + P);
           if (leader) mbar_arrive_expect_tx(bar(W_FULL + slot), 2 * kUnitBytes);
-          const uint32_t dst = w_base + slot * kUnitBytes;
-          tma_load_2d_2sm(dst, &tmW1, wfull[slot], (2 * h) * 64, j * 128 + (int)rank * 64);
-          tma_load_2d_2sm(dst + 8192, &tmW1, wfull[slot], (2 * h + 1) * 64, j * 128 + (int)rank * 64);
+          tma_load_2d_2sm(w_base + slot * kUnitBytes, &tmW1, wfull[slot], kb * 64, P * 256 + (int)rank * 128);
           advance();
         }
       };
@@ -193,17 +189,16 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       };
       for (int pr = pair0; pr < num_pairs; pr += pair_step) {
         load_fc1(0);
-        load_fc1(1);
-        for (int j = 0; j < kChunks; ++j) {
-          load_fc2(j);
-          if (j + 2 < kChunks) load_fc1(j + 2);
+        for (int P = 0; P < kChunks / 2; ++P) {
+          load_fc2(2 * P);
+          if (P + 1 < kChunks / 2) load_fc1(P + 1);
+          load_fc2(2 * P + 1);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader only) =====
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(256, 128, false, false);
       constexpr uint32_t idesc2 = make_idesc_bf16(256, 256, false, false);
       int slot = 0;
       uint32_t wphase = 0;
@@ -216,32 +211,30 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
         }
       };
       for (int pr = pair0; pr < num_pairs; pr += pair_step, ++n) {
-        // use counters: acc1 stage s / G buffer s are used by chunks j with j % 2 == s -> 4 uses per tile
-        auto fc1 = [&](int j) {
-          const int s = j & 1;
-          const uint32_t use = 4 * n + (j >> 1);
-          tr(100 + j);
-          mbar_wait_cluster(bar(T1_EMPTY + s), (use & 1) ^ 1);
-          tr(110 + j);
+        // fc1 group P: acc1 (256 columns, single stage) = m . W1[256 P .. 256 P + 255]^T, one N = 256 MMA series.
+        // (N = 128 MMAs re-read the 4 KB A slice per 2 KB of B and ran at half the N = 256 rate: the tensor pipe's
+        // operand fetch from shared memory, ~64 B/clk, is what bounds these shapes.)
+        auto fc1 = [&](int P) {
+          tr(100 + P);
+          mbar_wait_cluster(bar(T1_EMPTY), (P & 1) ^ 1);  // (4 uses per tile: parity of 4 n + P - 1)
+          tr(110 + P);
           tc_fence_after();
-          const uint32_t d = tmem_base + 256 + 128 * s;
-          for (int h = 0; h < 2; ++h) {
+          const uint32_t d = tmem_base + 256;
+          for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(bar(W_FULL + slot), wphase);
-            tr(120 + j);
+            tr(120 + P);
             tc_fence_after();
+            const uint32_t a_addr = a_base + kb * kUnitBytes;
+            const uint32_t b_addr = w_base + slot * kUnitBytes;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const int kb = 2 * h + (kk >> 2), k = kk & 3;
-              const uint32_t a_addr = a_base + kb * kUnitBytes + k * 32;
-              const uint32_t b_addr = w_base + slot * kUnitBytes + (kk >> 2) * 8192 + k * 32;
-              umma_bf16_2sm(d, make_desc_sw128(a_addr, 16, 1024), make_desc_sw128(b_addr, 16, 1024), idesc1,
-                            (h | kk) ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_2sm(d, make_desc_sw128(a_addr + k * 32, 16, 1024), make_desc_sw128(b_addr + k * 32, 16, 1024), idesc2,
+                            (kb | k) ? 1u : 0u);
             umma_commit_2sm(bar(W_EMPTY + slot), 3);
             advance();
           }
-          umma_commit_2sm(bar(T1_FULL + s), 3);
-          if (j == kChunks - 1) umma_commit_2sm(bar(A_EMPTY), 3);
+          umma_commit_2sm(bar(T1_FULL), 3);
+          if (P == kChunks / 2 - 1) umma_commit_2sm(bar(A_EMPTY), 3);
         };
         auto fc2 = [&](int j) {
           tr(200 + j);
@@ -271,10 +264,10 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
         tr(91);
         tc_fence_after();
         fc1(0);
-        fc1(1);
-        for (int j = 0; j < kChunks; ++j) {
-          fc2(j);
-          if (j + 2 < kChunks) fc1(j + 2);
+        for (int P = 0; P < kChunks / 2; ++P) {
+          fc2(2 * P);
+          if (P + 1 < kChunks / 2) fc1(P + 1);  // acc1 is free once the epilogue holds its second half in registers
+          fc2(2 * P + 1);
         }
       }
     }
@@ -305,7 +298,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const bool storer = (lane == 0 && quad == 0);  // one per part
-    const uint32_t t1_empty[2] = {lbar(T1_EMPTY), lbar(T1_EMPTY + 1)};
+    const uint32_t t1_empty = lbar(T1_EMPTY);
     const uint32_t g_full = lbar(G_FULL);
     const uint32_t t2_empty = lbar(T2_EMPTY);
     uint32_t n = 0;
@@ -328,19 +321,18 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       }
       // ---- GELU chunks: acc1[s] -> bf16 K-major tile G[s]; my 32 of the chunk's 128 columns ---------------------
       for (int j = 0; j < kChunks; ++j) {
-        const int s = j & 1;
-        const uint32_t use = 4 * n + (j >> 1);
+        const int s = j & 1;  // which 128-column half of acc1
         tr(400 + j);
-        mbar_wait(bar(T1_FULL + s), use & 1);
+        if (s == 0) mbar_wait(bar(T1_FULL), (j >> 1) & 1);  // fc1 group j/2 (parity of 4 n + j/2)
         tr(410 + j);
         tc_fence_after();
         tmem_ld32(tmem_base + lane_off + 256 + 128 * s + part * 32, v);
         const float* b1 = p.b1 + j * 128 + part * 32;  // kernel-parameter (constant bank) array, warp-uniform index
         tmem_ld_wait();
-        // the accumulator stage is free as soon as it sits in registers: fc1 of chunk j+2 may start
+        // acc1 is free as soon as its second half sits in registers: fc1 of the next group may start
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(t1_empty[s]);
+        if (s == 1 && lane == 0) mbar_arrive_remote(t1_empty);
         const uint32_t grow = g_base + (part >> 1) * kUnitBytes + row * 128;
         uint32_t o[16];
 #pragma unroll

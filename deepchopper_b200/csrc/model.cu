@@ -281,7 +281,7 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_fc1, lw.w_fc1, kInner, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_fc2, lw.w_fc2, kD, kInner, 256));
-    DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 64));
+    DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
   }
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.weight", kD, &w->lnf_g));
