@@ -601,6 +601,27 @@ int make_tmap_3d_cm(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, ui
 }
 
 
+// bf16 [B][C][L] (L contiguous); box = 64 (L) x 128 (C) x 1: 128 channel rows of 64 tokens (in_proj epilogue stores)
+int make_tmap_3d_chbox(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return DCB200_ECUDA;
+  }
+  cuuint64_t dims[3] = {L, C, B};
+  cuuint64_t strides[2] = {L * 2, C * L * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d chbox) failed: %d", (int)r);
+    return DCB200_ECUDA;
+  }
+  return DCB200_OK;
+}
+
 // bf16 [B][C][L] (L contiguous); box = 64 (L) x 1 (C) x 128 (B), 128B swizzle: a K-major operand tile whose
 // rows are batch rows of one channel
 int make_tmap_3d_rows(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L) {

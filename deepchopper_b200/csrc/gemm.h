@@ -31,6 +31,7 @@ int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorM
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int make_tmap_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols);
 int make_tmap_3d_cm(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L);
+int make_tmap_3d_chbox(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L);
 int make_tmap_3d_rows(CUtensorMap* m, const void* base, uint64_t B, uint64_t C, uint64_t L);
 
 }  // namespace dcb

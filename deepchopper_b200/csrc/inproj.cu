@@ -1,0 +1,319 @@
+// Hyena operator front end, fused (HF modeling_hyena.py HyenaOperator.forward up to the long conv):
+//   z = in_linear(u)  (256 -> 768)          zc = short depthwise conv (3 taps, causal) of z
+//   x0, x1, v = split(zc)                   vv = v * x1 ,  gate = x0          -> both bf16 channel-major [B,256,L]
+// replacing gemm_kernel<INPROJ> + shortconv_gate_kernel: z ([B,768,L] bf16, 1.5 KB per token written and read back)
+// never exists.  HBM traffic per token: read u (512 B), write vv + gate (1 KB).
+//
+// One persistent CTA per SM.  A work unit is (128-token tile, 128-channel group): three tcgen05 MMA series
+//   x1 = W_in[256+c..] . u^T ,  v = W_in[512+c..] . u^T ,  x0 = W_in[c..] . u^T        (M = 128 channels, K = 256)
+// with N = 144 tokens: the tile plus the 16 tokens before it, so the causal 3-tap convolution (which needs z[t-1],
+// z[t-2]) has its halo in the same accumulator and tiles stay independent.  The accumulator rows are channels, so an
+// epilogue thread owns one channel and walks consecutive tokens: the convolution is register arithmetic.
+//
+//   TMEM   three 144-column regions X1 | V | X0 (stride 160), each with its own full/empty barrier: the MMA warp is
+//          at most one series ahead of the epilogue (VV epilogue runs under the x0 series, G epilogue under the next x1)
+//   smem   u tile 4 x 18 KB (K boxes of 144 token rows, refilled box by box as the tile's last series retires)
+//          W ring 4 x 16 KB | 4 x 16 KB output staging (TMA-stored boxes 64 tokens x 128 channels) | per-channel consts
+//   warp 0 producer (u boxes + W ring)   warp 1 MMA issuer   warp 2 TMEM allocator   warps 4-11 epilogue
+#include "common.cuh"
+#include "gemm.h"
+#include "inproj.h"
+#include "ptx.cuh"
+
+namespace dcb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kN = 144;                       // tokens per MMA: 16 halo + 128
+constexpr int kHalo = 16;
+constexpr uint32_t kUBox = kN * 128;          // 18 KB: 144 token rows x 64 k
+constexpr uint32_t kWBox = 128 * 128;         // 16 KB: 128 channel rows x 64 k
+constexpr int kWStages = 4;
+constexpr uint32_t kOutBox = 128 * 128;       // 16 KB: 128 channel rows x 64 tokens (bf16)
+constexpr int kRegionStride = 160;
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// two columns of 32-bit: the convolution halo
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+
+// causal 3-tap conv of 32 consecutive tokens given z[t-2], z[t-1] (h0, h1) and z[0..31]; out may alias nothing
+__device__ __forceinline__ void sconv32(const float (&z)[32], float h0, float h1, float w0, float w1, float w2, float cb,
+                                        float (&out)[32]) {
+  out[0] = fmaf(w0, h0, fmaf(w1, h1, fmaf(w2, z[0], cb)));
+  out[1] = fmaf(w0, h1, fmaf(w1, z[0], fmaf(w2, z[1], cb)));
+#pragma unroll
+  for (int i = 2; i < 32; ++i) out[i] = fmaf(w0, z[i - 2], fmaf(w1, z[i - 1], fmaf(w2, z[i], cb)));
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmVV, const __grid_constant__ CUtensorMap tmGate,
+                   const InprojParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t u_base = smem_u32(smem);                       // 4 x 18 KB (each 1024-aligned: 18 KB = 18 x 1024)
+  const uint32_t w_base = u_base + 4 * kUBox;
+  const uint32_t o_base = w_base + kWStages * kWBox;            // 4 output boxes: VV h0, VV h1, G h0, G h1
+  float* cst = reinterpret_cast<float*>(smem + 4 * kUBox + kWStages * kWBox + 4 * kOutBox);  // [768][5]: b_in, w0, w1, w2, cb
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 768 * 5);
+  const uint32_t bar_base = smem_u32(bars);
+  enum { U_FULL = 0, U_EMPTY = 4, W_FULL = 8, W_EMPTY = W_FULL + kWStages, R_FULL = W_EMPTY + kWStages, R_EMPTY = R_FULL + 3,
+         N_BARS = R_EMPTY + 3 };
+  auto bar = [&](int i) { return bar_base + 8u * i; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + N_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmU);
+    prefetch_tmap(&tmW);
+    prefetch_tmap(&tmVV);
+    prefetch_tmap(&tmGate);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bar(U_FULL + s), 1);
+      mbar_init(bar(U_EMPTY + s), 1);
+    }
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(bar(W_FULL + s), 1);
+      mbar_init(bar(W_EMPTY + s), 1);
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(bar(R_FULL + s), 1);
+      mbar_init(bar(R_EMPTY + s), 8);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  // per-channel constants: z = acc + b_in ; zc[t] = w0 z[t-2] + w1 z[t-1] + w2 z[t] + cb
+  for (int i = threadIdx.x; i < 768; i += kThreads) {
+    cst[i * 5 + 0] = p.b_in[i];
+    cst[i * 5 + 1] = p.short_w[i * 3 + 0];
+    cst[i * 5 + 2] = p.short_w[i * 3 + 1];
+    cst[i * 5 + 3] = p.short_w[i * 3 + 2];
+    cst[i * 5 + 4] = p.short_b[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int num_tiles = p.num_tiles;
+
+  // series order within a unit (token tile, channel group g): x1, v, x0  ->  TMEM region = series index
+  // W_in row offset of series s for group g: x1 -> 256, v -> 512, x0 -> 0   (+ 128 g)
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wphase = 0, n = 0;
+      for (int o = blockIdx.x; o < num_tiles; o += gridDim.x, ++n) {
+        const int tok0 = o * 128;
+        for (int g = 0; g < 2; ++g) {
+          for (int s = 0; s < 3; ++s) {
+            const int wrow = (s == 0 ? 256 : (s == 1 ? 512 : 0)) + 128 * g;
+            for (int kb = 0; kb < 4; ++kb) {
+              if (g == 0 && s == 0) {  // this tile's u box kb (its previous content retired with the last series)
+                mbar_wait(bar(U_EMPTY + kb), (n & 1) ^ 1);
+                mbar_arrive_expect_tx(bar(U_FULL + kb), kUBox);
+                tma_load_2d(u_base + kb * kUBox, &tmU, bar(U_FULL + kb), kb * 64, tok0 - kHalo);
+              }
+              mbar_wait(bar(W_EMPTY + stage), wphase ^ 1);
+              mbar_arrive_expect_tx(bar(W_FULL + stage), kWBox);
+              tma_load_2d(w_base + stage * kWBox, &tmW, bar(W_FULL + stage), kb * 64, wrow);
+              if (++stage == kWStages) {
+                stage = 0;
+                wphase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kN, false, false);
+      int stage = 0;
+      uint32_t wphase = 0, n = 0;
+      uint32_t use = 0;  // units started (each region is used once per unit)
+      for (int o = blockIdx.x; o < num_tiles; o += gridDim.x, ++n) {
+        for (int g = 0; g < 2; ++g, ++use) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(bar(R_EMPTY + s), (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + s * kRegionStride;
+            for (int kb = 0; kb < 4; ++kb) {
+              if (g == 0 && s == 0) mbar_wait(bar(U_FULL + kb), n & 1);
+              mbar_wait(bar(W_FULL + stage), wphase);
+              tc_fence_after();
+              const uint32_t a_addr = w_base + stage * kWBox;
+              const uint32_t b_addr = u_base + kb * kUBox;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d, make_desc_sw128(a_addr + k * 32, 16, 1024), make_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
+                          (kb | k) ? 1u : 0u);
+              umma_commit(bar(W_EMPTY + stage));
+              if (g == 1 && s == 2) umma_commit(bar(U_EMPTY + kb));  // last series of the tile: u box kb may be refilled
+              if (++stage == kWStages) {
+                stage = 0;
+                wphase ^= 1;
+              }
+            }
+            umma_commit(bar(R_FULL + s));
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;      // tokens [64 half, 64 half + 64) of the tile
+    const int row = quad * 32 + lane;      // channel within the group
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const bool storer = (quad == 0 && lane == 0);  // one per half
+    uint32_t use = 0;
+    for (int o = blockIdx.x; o < num_tiles; o += gridDim.x) {
+      const int tok0 = o * 128;
+      const int b = tok0 / p.L, l0 = tok0 % p.L;
+      const bool row_start = (l0 == 0);  // conv zero padding: the halo columns then hold the previous read's tail
+      for (int g = 0; g < 2; ++g, ++use) {
+        const int ch = g * 128 + row;  // my channel within each third
+        // ---- VV: sc(x1) * sc(v) ----------------------------------------------------------------------------------
+        {
+          const float* c1 = cst + (256 + ch) * 5;
+          const float* cv = cst + (512 + ch) * 5;
+          const float b1 = c1[0], w10 = c1[1], w11 = c1[2], w12 = c1[3], cb1 = c1[4];
+          const float bv = cv[0], wv0 = cv[1], wv1 = cv[2], wv2 = cv[3], cbv = cv[4];
+          mbar_wait(bar(R_FULL + 0), use & 1);
+          mbar_wait(bar(R_FULL + 1), use & 1);
+          tc_fence_after();
+          const uint32_t t_x1 = tmem_base + lane_off + 0 * kRegionStride + kHalo + 64 * half;
+          const uint32_t t_v = tmem_base + lane_off + 1 * kRegionStride + kHalo + 64 * half;
+          const uint32_t obox = o_base + half * kOutBox + row * 128;
+          // wait until the previous unit's store from this box has finished reading it
+          if (storer) bulk_wait_read<1>();
+          bar_sync(2 + half, 128);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t ra[32], rb[32], ha0, ha1, hb0, hb1;
+            tmem_ld32(t_x1 + 32 * sub, ra);
+            tmem_ld2(t_x1 + 32 * sub - 2, ha0, ha1);
+            tmem_ld32(t_v + 32 * sub, rb);
+            tmem_ld2(t_v + 32 * sub - 2, hb0, hb1);
+            tmem_ld_wait();
+            float z[32], c1o[32], cvo[32];
+            const bool zero_halo = row_start && half == 0 && sub == 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(ra[i]) + b1;
+            sconv32(z, zero_halo ? 0.f : __uint_as_float(ha0) + b1, zero_halo ? 0.f : __uint_as_float(ha1) + b1, w10, w11, w12, cb1,
+                    c1o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(rb[i]) + bv;
+            sconv32(z, zero_halo ? 0.f : __uint_as_float(hb0) + bv, zero_halo ? 0.f : __uint_as_float(hb1) + bv, wv0, wv1, wv2, cbv,
+                    cvo);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4), pack_bf16(c1o[8 * q] * cvo[8 * q], c1o[8 * q + 1] * cvo[8 * q + 1]),
+                     pack_bf16(c1o[8 * q + 2] * cvo[8 * q + 2], c1o[8 * q + 3] * cvo[8 * q + 3]),
+                     pack_bf16(c1o[8 * q + 4] * cvo[8 * q + 4], c1o[8 * q + 5] * cvo[8 * q + 5]),
+                     pack_bf16(c1o[8 * q + 6] * cvo[8 * q + 6], c1o[8 * q + 7] * cvo[8 * q + 7]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar(R_EMPTY + 0));
+            mbar_arrive(bar(R_EMPTY + 1));
+          }
+          fence_proxy_async();
+          bar_sync(2 + half, 128);
+          if (storer) {
+            tma_store_3d(&tmVV, o_base + half * kOutBox, l0 + 64 * half, g * 128, b);
+            bulk_commit();
+          }
+        }
+        // ---- G: sc(x0) ---------------------------------------------------------------------------------------------
+        {
+          const float* c0 = cst + ch * 5;
+          const float b0 = c0[0], w0 = c0[1], w1 = c0[2], w2 = c0[3], cb0 = c0[4];
+          mbar_wait(bar(R_FULL + 2), use & 1);
+          tc_fence_after();
+          const uint32_t t_x0 = tmem_base + lane_off + 2 * kRegionStride + kHalo + 64 * half;
+          const uint32_t obox = o_base + (2 + half) * kOutBox + row * 128;
+          if (storer) bulk_wait_read<1>();
+          bar_sync(2 + half, 128);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t ra[32], ha0, ha1;
+            tmem_ld32(t_x0 + 32 * sub, ra);
+            tmem_ld2(t_x0 + 32 * sub - 2, ha0, ha1);
+            tmem_ld_wait();
+            float z[32], co[32];
+            const bool zero_halo = row_start && half == 0 && sub == 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(ra[i]) + b0;
+            sconv32(z, zero_halo ? 0.f : __uint_as_float(ha0) + b0, zero_halo ? 0.f : __uint_as_float(ha1) + b0, w0, w1, w2, cb0, co);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4), pack_bf16(co[8 * q], co[8 * q + 1]),
+                     pack_bf16(co[8 * q + 2], co[8 * q + 3]), pack_bf16(co[8 * q + 4], co[8 * q + 5]),
+                     pack_bf16(co[8 * q + 6], co[8 * q + 7]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(R_EMPTY + 2));
+          fence_proxy_async();
+          bar_sync(2 + half, 128);
+          if (storer) {
+            tma_store_3d(&tmGate, o_base + (2 + half) * kOutBox, l0 + 64 * half, g * 128, b);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (storer) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorMap& tm_w, const CUtensorMap& tm_vv,
+                       const CUtensorMap& tm_gate, const InprojParams& p) {
+  const size_t smem = 4 * kUBox + kWStages * kWBox + 4 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    DCB_CUDA(cudaFuncSetAttribute(inproj_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  ProfScope prof(ctx, K_INPROJ);
+  inproj_conv_kernel<<<grid, kThreads, smem, ctx->stream>>>(tm_u, tm_w, tm_vv, tm_gate, p);
+  DCB_LAUNCH_CHECK(ctx);
+  return DCB200_OK;
+}
+
+}  // namespace dcb

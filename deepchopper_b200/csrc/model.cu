@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "fftconv.h"
 #include "gemm.h"
+#include "inproj.h"
 #include "mlp.h"
 #include "toeplitz.h"
 
@@ -404,7 +405,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   __nv_bfloat16* g = bg.as<__nv_bfloat16>();
 
   __nv_bfloat16 *vv = nullptr, *gate = nullptr;
-  CUtensorMap tm_vv, tm_gate, tm_yr;
+  CUtensorMap tm_vv, tm_gate, tm_yr, tm_vv_st, tm_gate_st, tm_u144;
   if (toep) {
     DevBuf& bvv = ctx->buf("act_vv");
     DevBuf& bgt = ctx->buf("act_gate");
@@ -415,6 +416,9 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     DCB_CHECK(make_tmap_3d_rows(&tm_vv, vv, B, kD, L));
     DCB_CHECK(make_tmap_3d_rows(&tm_gate, gate, B, kD, L));
     DCB_CHECK(make_tmap_3d_rows(&tm_yr, y, B, kD, L));
+    DCB_CHECK(make_tmap_3d_chbox(&tm_vv_st, vv, B, kD, L));
+    DCB_CHECK(make_tmap_3d_chbox(&tm_gate_st, gate, B, kD, L));
+    DCB_CHECK(make_tmap_2d(&tm_u144, u, T, kD, 144));
   }
   CUtensorMap tm_u, tm_y, tm_g, tm_hA, tm_hB;
   DCB_CHECK(make_tmap_2d_f32(&tm_hA, hA, T, kD));
@@ -443,15 +447,22 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   for (int l = 0; l < kLayers; ++l) {
     LayerW& lw = w->layer[l];
     GemmParams p = gp;
-    p.bias = lw.b_in;
-    p.out_bf16 = z;
-    DCB_CHECK(launch_gemm(ctx, G_INPROJ, lw.tm_in, tm_u, p));
-    DCB_STAGE_DONE();
-
     if (toep) {
-      DCB_CHECK(launch_shortconv_gate(ctx, z, lw.short_w, lw.short_b, B, L, vv, gate));
+      // in_proj + short conv + first gate in one kernel: z never exists
+      InprojParams ip;
+      ip.num_tiles = (int)(T / 128);
+      ip.L = L;
+      ip.b_in = lw.b_in;
+      ip.short_w = lw.short_w;
+      ip.short_b = lw.short_b;
+      DCB_CHECK(launch_inproj_conv(ctx, tm_u144, lw.tm_in, tm_vv_st, tm_gate_st, ip));
+      DCB_STAGE_DONE();
       DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, tm_vv, tm_gate, tm_yr, B, L));
     } else {
+      p.bias = lw.b_in;
+      p.out_bf16 = z;
+      DCB_CHECK(launch_gemm(ctx, G_INPROJ, lw.tm_in, tm_u, p));
+      DCB_STAGE_DONE();
       ConvParams cp;
       cp.z = z;
       cp.y = y;

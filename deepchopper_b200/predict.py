@@ -52,6 +52,10 @@ def plan_batches(lens: np.ndarray, token_budget: int = 512 * 1024, max_rows: int
                 break
             mx = m2
             j += 1
+        # the long-convolution kernel works on 128-row tiles of one channel: keep full tiles when the batch is large
+        if sort and j - i > ROW_TILE and j < n:
+            j = i + (j - i) // ROW_TILE * ROW_TILE
+            mx = int(lens[order[j - 1]])
         lpad = mx + 1
         batches.append(Batch(order[i:j].copy(), lpad, (lpad + ROW_TILE - 1) // ROW_TILE * ROW_TILE))
         i = j

@@ -103,9 +103,19 @@ def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
         close("ln1", u, lay.norm1(emb), 1e-2, 1e-2)
         # stage 1: in_proj (oracle op applied to the GPU's own bf16 input isolates the kernel)
         run_debug(gpu, tok, qd, 1)
-        z = read_ws(gpu, "act_z", (B, 768, L), "bf16")
         z_ref = F.linear(u, bf(lay.mixer.in_linear.weight), lay.mixer.in_linear.bias).transpose(1, 2)
-        close("in_proj", z, z_ref, 2e-2, 1e-2)
+        if conv_kind == "fft":
+            z = read_ws(gpu, "act_z", (B, 768, L), "bf16")
+            close("in_proj", z, z_ref, 2e-2, 1e-2)
+        else:
+            # fused front end: in_proj + short conv + first gate; z stays on chip in fp32
+            z = z_ref
+            zc = lay.mixer.short_filter(z)[..., :L]
+            x0r, x1r, vr = zc.split(256, dim=1)
+            vv = read_ws(gpu, "act_vv", (B, 256, L), "bf16")
+            gate = read_ws(gpu, "act_gate", (B, 256, L), "bf16")
+            close("gate", gate, x0r, 1e-2, 1e-2)
+            close("vv", vv, vr * x1r, 1e-2, 1e-2)
         # stage 2: short conv + gate + long conv + gate
         run_debug(gpu, tok, qd, 2)
         y = read_ws(gpu, "act_y", (B, 256, L), "bf16")
@@ -113,7 +123,7 @@ def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
         x0, x1, v = zc.split(256, dim=1)
         k = lay.mixer.filter_fn.filter(L)[0].transpose(0, 1)
         y_ref = H.fftconv_ref(v * x1, k, lay.mixer.filter_fn.bias) * x0
-        # bf16 z in, bf16 y out (and bf16 filter taps on the Toeplitz path): ~0.4 % of the local signal scale
+        # bf16 activations in and out (and bf16 filter taps on the Toeplitz path): ~0.4 % of the local signal scale
         close("hyena_conv", y, y_ref, 3e-2 * y_ref.pow(2).mean().sqrt().item() + 1e-3, 2e-2)
         # stage 3: out_proj + residual + LN2
         run_debug(gpu, tok, qd, 3)
