@@ -31,11 +31,12 @@ METRIC = "bases_per_sec_predict_smooth"
 UNIT = "bases/s"
 
 # algorithmic work per padded token (SURVEY §8d / DESIGN.md), used for the roofline figures
-FLOPS_PER_TOKEN = {"mlp": 2 * 2 * 256 * 1024, "in_proj": 2 * 256 * 768, "out_proj": 2 * 256 * 256, "fc1": 2 * 256 * 1024, "fc2": 2 * 1024 * 256,
+FLOPS_PER_TOKEN = {"mlp": 2 * 2 * 256 * 1024,              # fused fc1 + GELU + fc2 + residual + LN
+                   "in_proj": 2 * 256 * 768,               # fused with the short conv + first gate (Toeplitz path)
+                   "out_proj": 2 * 256 * 256,
                    "head1": 2 * 256 * 1024, "head2": 2 * (1024 * 1024 + 2 * 1024)}
-BYTES_PER_TOKEN = {"hyena_conv": 768 * 2 + 256 * 2,        # FFT path: read z (3 channels) + write y, bf16
-                   "shortconv_gate": 768 * 2 + 2 * 256 * 2,  # read z, write vv + gate
-                   "toeplitz_conv": 3 * 256 * 2,             # read vv + gate, write y (Toeplitz blocks stay in L2)
+BYTES_PER_TOKEN = {"hyena_conv": 768 * 2 + 256 * 2,        # FFT fallback: read z (3 channels) + write y, bf16
+                   "toeplitz_conv": 3 * 256 * 2,             # read vv + gate, write y (the Toeplitz table stays in L2)
                    "embed_ln": 1 + 256 * 4 + 256 * 2,      # token in, fp32 residual + bf16 LN out
                    "encode": 2 + 1 + 4,                     # seq+qual chars in, token + fp32 quality out
                    "smooth_chop": 1}                        # int8 label in (coordinates out are O(reads))

@@ -13,8 +13,6 @@
 //            the accumulator rows are channels and a thread writes contiguous tokens)
 //   OUTPROJ  h' = y . W_o^T + b + h ; m = LN2(h')   (A = y read MN-major straight from the conv's
 //            channel-major output: no transpose pass)
-//   FC1      g = gelu_tanh(m . W1^T + b1)   -> bf16 [T,1024]
-//   FC2      h'' = g . W2^T + b2 + h' ; u = LN(h'')  (next layer's LN1, or ln_f after the last layer)
 //   HEAD1    r = relu(hf . Wh1^T + b1) + q  -> bf16 [T,1024]        (head.py:94-97)
 //   HEAD2    o = relu(r . Wh2^T + b2 + r) ; logits = o . W3^T + b3 ; label = l1 > l0   (head.py:98-102)
 #include "common.cuh"
@@ -36,22 +34,12 @@ constexpr int kVecFloats = 3 * 1024;                // column vectors cached in 
 template <int MODE> struct Traits;
 template <> struct Traits<G_INPROJ>  { static constexpr int K = 256,  NT = 128, INNER = 6, STAGES = 4; static constexpr bool A_MN = false; };
 template <> struct Traits<G_OUTPROJ> { static constexpr int K = 256,  NT = 256, INNER = 1, STAGES = 3; static constexpr bool A_MN = true;  };
-template <> struct Traits<G_FC1>     { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
-template <> struct Traits<G_FC2>     { static constexpr int K = 1024, NT = 256, INNER = 1, STAGES = 3; static constexpr bool A_MN = false; };
 template <> struct Traits<G_HEAD1>   { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
 template <> struct Traits<G_HEAD2>   { static constexpr int K = 1024, NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   (F.gelu(approximate="tanh"))
-  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -108,13 +96,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   // column vectors -> smem (epilogue warps read them as broadcast / lane-fixed float4)
-  if (MODE == G_OUTPROJ || MODE == G_FC2) {
+  if (MODE == G_OUTPROJ) {
     for (int i = threadIdx.x; i < 256; i += kThreads) {
       vec[i] = p.bias[i];
       vec[1024 + i] = p.ln_g[i];
       vec[2048 + i] = p.ln_b[i];
     }
-  } else if (MODE == G_FC1 || MODE == G_HEAD1) {
+  } else if (MODE == G_HEAD1) {
     for (int i = threadIdx.x; i < 1024; i += kThreads) vec[i] = p.bias[i];
   } else if (MODE == G_HEAD2) {
     for (int i = threadIdx.x; i < 1024; i += kThreads) {
@@ -223,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t tile_parity = 0;
     uint32_t v[32];
     float4 rpre0[8], rpre1[8];  // LN modes: residual of the next two column chunks (T layout)
-    if ((MODE == G_OUTPROJ || MODE == G_FC2) && (int)blockIdx.x < num_outer) {  // (LN modes only)
+    if (MODE == G_OUTPROJ && (int)blockIdx.x < num_outer) {  // (LN modes only)
       const size_t r0 = (size_t)blockIdx.x * kTileM + quad * 32 + trow0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -241,7 +229,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * NT + half * HALF + ((uint32_t)(quad * 32) << 16);
 
-        if (MODE == G_INPROJ || MODE == G_FC1 || MODE == G_HEAD1) {
+        if (MODE == G_INPROJ || MODE == G_HEAD1) {
           // ---- bf16 output, element-wise epilogue: 64 columns (128 B of bf16) per staged group -------------
           const size_t own_row = (size_t)tok0 + quad * 32 + lane;
           float rowv = 0.f;  // INPROJ: bias of my channel row; HEAD1: quality of my token row
@@ -266,7 +254,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     const float x = __uint_as_float(v[q * 8 + j]) + bj[j];
-                    y[j] = (MODE == G_FC1) ? gelu_tanh(x) : (fmaxf(x, 0.f) + rowv);
+                    y[j] = fmaxf(x, 0.f) + rowv;
                   }
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + c * 64 + q * 16),
@@ -295,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             __syncwarp();
           }
-        } else if (MODE == G_OUTPROJ || MODE == G_FC2) {
+        } else if (MODE == G_OUTPROJ) {
           // ---- + bias + residual -> h (fp32), LayerNorm -> bf16 ------------------------------------------------
           // Global I/O in the T layout (whole 128-byte lines per instruction); the residual of the next two
           // column chunks is prefetched into registers (memory-level parallelism: these kernels are
@@ -500,7 +488,7 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
     configured = true;
   }
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
-  static const int kinds[6] = {K_INPROJ, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2};
+  static const int kinds[4] = {K_INPROJ, K_OUTPROJ, K_HEAD1, K_HEAD2};
   ProfScope prof(ctx, kinds[MODE]);
   gemm_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(a, b, p);
   DCB_LAUNCH_CHECK(ctx);
@@ -511,8 +499,6 @@ int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorM
   switch (mode) {
     case G_INPROJ: return launch_mode<G_INPROJ>(ctx, a, b, p);
     case G_OUTPROJ: return launch_mode<G_OUTPROJ>(ctx, a, b, p);
-    case G_FC1: return launch_mode<G_FC1>(ctx, a, b, p);
-    case G_FC2: return launch_mode<G_FC2>(ctx, a, b, p);
     case G_HEAD1: return launch_mode<G_HEAD1>(ctx, a, b, p);
     case G_HEAD2: return launch_mode<G_HEAD2>(ctx, a, b, p);
   }

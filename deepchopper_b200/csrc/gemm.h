@@ -7,7 +7,7 @@ struct dcb200_ctx;
 
 namespace dcb {
 
-enum GemmMode { G_INPROJ = 0, G_OUTPROJ = 1, G_FC1 = 2, G_FC2 = 3, G_HEAD1 = 4, G_HEAD2 = 5 };
+enum GemmMode { G_INPROJ = 0, G_OUTPROJ = 1, G_HEAD1 = 2, G_HEAD2 = 3 };
 
 struct GemmParams {
   int T;          // tokens = B * L (multiple of 128)

@@ -33,7 +33,7 @@ struct LayerW {
   float* k = nullptr;  // [256][Lmax] implicit filter, evaluated once
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
   __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
-  CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
+  CUtensorMap tm_in, tm_out;
   std::vector<float> hb_fc1, hb_fc2, h_ln1_g, h_ln1_b;  // host copies: passed to kernels as constant-bank parameters
   CUtensorMap tm_w1u, tm_w2u;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
 };
@@ -51,6 +51,7 @@ struct dcb200_weights {
   float *bh1 = nullptr, *bh2 = nullptr, *w3 = nullptr, *b3 = nullptr;
   CUtensorMap tm_h1, tm_h2;
   std::map<int, float2*> tw;  // per FFT size N: exp(-2 pi i k/N)
+  int toep_cap = 0;           // read length the Toeplitz tables were built for
   std::vector<void*> allocs;
 };
 
@@ -280,8 +281,6 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_LAUNCH_CHECK(ctx);
     DCB_CHECK(make_tmap_2d(&lw.tm_in, lw.w_in, 3 * kD, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
-    DCB_CHECK(make_tmap_2d(&lw.tm_fc1, lw.w_fc1, kInner, kD, 256));
-    DCB_CHECK(make_tmap_2d(&lw.tm_fc2, lw.w_fc2, kD, kInner, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
   }
@@ -337,16 +336,20 @@ static int ensure_fft_size(dcb200_ctx* ctx, dcb200_weights* w, int N) {
   return DCB200_OK;
 }
 
-// Toeplitz core-matrix tables of all layers (35 MB each), built on first use
-static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w) {
-  if (w->layer[0].toep) return DCB200_OK;
+// Toeplitz core-matrix tables of all layers, built on first use for reads up to 8192 tokens (35 MB per layer) and
+// rebuilt for the model's full 32768 (135 MB per layer) the first time a longer batch arrives
+static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w, int L) {
+  if (w->toep_cap >= L) return DCB200_OK;
+  const int cap = L <= 8192 ? 8192 : kToepMaxL;
   for (int l = 0; l < kLayers; ++l) {
     void* t = nullptr;
-    DCB_CUDA(cudaMalloc(&t, toeplitz_table_bytes()));
-    w->allocs.push_back(t);
-    DCB_CHECK(launch_toeplitz_table(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, static_cast<__nv_bfloat16*>(t)));
+    DCB_CUDA(cudaMalloc(&t, toeplitz_table_bytes(cap)));
+    w->allocs.push_back(t);  // (a superseded smaller table is released with the weights)
+    DCB_CHECK(launch_toeplitz_table(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, cap,
+                                    static_cast<__nv_bfloat16*>(t)));
     w->layer[l].toep = static_cast<__nv_bfloat16*>(t);
   }
+  w->toep_cap = cap;
   return DCB200_OK;
 }
 
@@ -377,12 +380,12 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   while (N < 2 * L) N <<= 1;
   if (!toep) {
     if (conv_smem_bytes(N, L) > 227 * 1024) {
-      set_error("L=%d: long-read (> 8192 tokens) convolution path is not built yet", L);
+      set_error("L=%d: the FFT fallback kernel holds at most 8192 tokens; use the default (Toeplitz) path", L);
       return DCB200_EINVAL;
     }
     DCB_CHECK(ensure_fft_size(ctx, w, N));
   } else {
-    DCB_CHECK(ensure_toeplitz(ctx, w));
+    DCB_CHECK(ensure_toeplitz(ctx, w, L));
   }
   const size_t T = (size_t)B * L;
   DevBuf& bhA = ctx->buf("act_hA");
@@ -394,7 +397,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   DCB_CHECK(bhA.reserve(T * kD * 4));
   DCB_CHECK(bhB.reserve(T * kD * 4));
   DCB_CHECK(bu.reserve(T * kD * 2));
-  DCB_CHECK(bz.reserve(T * 3 * kD * 2));
+  if (!toep) DCB_CHECK(bz.reserve(T * 3 * kD * 2));  // z only exists on the FFT fallback path
   DCB_CHECK(by.reserve(T * kD * 2));
   DCB_CHECK(bg.reserve(T * kInner * 2));
   float* hA = bhA.as<float>();
@@ -423,8 +426,6 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   CUtensorMap tm_u, tm_y, tm_g, tm_hA, tm_hB;
   DCB_CHECK(make_tmap_2d_f32(&tm_hA, hA, T, kD));
   DCB_CHECK(make_tmap_2d_f32(&tm_hB, hB, T, kD));
-  const char* mlp_env = getenv("DCB200_MLP");
-  const bool fused_mlp = !(mlp_env && !strcmp(mlp_env, "unfused"));
   DCB_CHECK(make_tmap_2d(&tm_u, u, T, kD, 128));
   DCB_CHECK(make_tmap_3d_cm(&tm_y, y, B, kD, L));
   DCB_CHECK(make_tmap_2d(&tm_g, g, T, kInner, 128));
@@ -457,7 +458,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       ip.short_b = lw.short_b;
       DCB_CHECK(launch_inproj_conv(ctx, tm_u144, lw.tm_in, tm_vv_st, tm_gate_st, ip));
       DCB_STAGE_DONE();
-      DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, tm_vv, tm_gate, tm_yr, B, L));
+      DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, w->toep_cap, tm_vv, tm_gate, tm_yr, B, L));
     } else {
       p.bias = lw.b_in;
       p.out_bf16 = z;
@@ -487,9 +488,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     DCB_CHECK(launch_gemm(ctx, G_OUTPROJ, tm_y, lw.tm_out, p));
     DCB_STAGE_DONE();
 
-    const float* nln_g = (l + 1 < kLayers) ? w->layer[l + 1].ln1_g : w->lnf_g;
-    const float* nln_b = (l + 1 < kLayers) ? w->layer[l + 1].ln1_b : w->lnf_b;
-    if (fused_mlp) {
+    {
       static thread_local MlpParams mp;  // 7 KB: keep it off the stack
       mp.num_pairs = (int)((T / 128 + 1) / 2);
       mp.T = (int)T;
@@ -509,22 +508,6 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       }
       DCB_CHECK(launch_mlp(ctx, tm_u, lw.tm_w1u, lw.tm_w2u, tm_hB, tm_hA, tm_u, mp));
       DCB_STAGE_DONE();
-      DCB_STAGE_DONE();
-    } else {
-      p = gp;
-      p.bias = lw.b_fc1;
-      p.out_bf16 = g;
-      DCB_CHECK(launch_gemm(ctx, G_FC1, tm_u, lw.tm_fc1, p));
-      DCB_STAGE_DONE();
-
-      p = gp;
-      p.bias = lw.b_fc2;
-      p.resid = hB;
-      p.h_out = hA;  // (the last layer's value is not consumed again, but the epilogue stages through it)
-      p.ln_g = nln_g;
-      p.ln_b = nln_b;
-      p.out_bf16 = u;
-      DCB_CHECK(launch_gemm(ctx, G_FC2, tm_g, lw.tm_fc2, p));
       DCB_STAGE_DONE();
     }
   }

@@ -14,7 +14,7 @@
 // address selects Q.  A 64-token K chunk touches a window of 40 consecutive core matrices (5 KB), which the producer
 // bulk-copies from the (L2-resident, 16 L bytes per channel) table next to the 16 KB A tile of the same pipeline
 // stage, so HBM traffic stays at the algorithmic minimum: read vv and gate, write y.  Causality (s > t) falls out of
-// the zero taps.  Cost grows with L (64 KFLOP x (L/128 + 1)/2 per token); used up to L = 8192.
+// the zero taps.  Cost grows with L (64 KFLOP x (L/128 + 1)/2 per token).
 //
 //   warp 0   producer: per stage one A tile (3-D TMA box 64 tokens x 1 channel x 128 rows) + its E window
 //   warp 1   MMA issuer (tcgen05.mma M=128, N=256 / 128 on the diagonal block, K=16)
@@ -38,16 +38,17 @@ constexpr int kTzGSlots = 3;    // 16 KB each
 constexpr int kTzZeroChunks = 32;
 constexpr uint32_t kTzBox = 128 * 128;  // bytes of one TMA box
 
-// E table: [256 channels][kToepMaxL/8 + 32 chunks][8 rows][8 cols] bf16, chunk position p <-> i = kToepMaxL/8 - 1 - p
+// E table: [256 channels][cap/8 + 32 chunks][8 rows][8 cols] bf16, chunk position p <-> i = cap/8 - 1 - p
 __global__ void __launch_bounds__(256) toeplitz_table_kernel(const float* __restrict__ k, int k_stride, int k_len,
-                                                             const float* __restrict__ D, __nv_bfloat16* __restrict__ E) {
-  constexpr int P = kToepMaxL / 8 + kTzZeroChunks;
+                                                             const float* __restrict__ D, int cap,
+                                                             __nv_bfloat16* __restrict__ E) {
+  const int P = cap / 8 + kTzZeroChunks;
   const int c = blockIdx.y;
   const float* kc = k + (size_t)c * k_stride;
   __nv_bfloat16* dst = E + (size_t)c * P * 64;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P * 64; idx += gridDim.x * blockDim.x) {
     const int p = idx >> 6, r = (idx >> 3) & 7, cc = idx & 7;
-    const int i = kToepMaxL / 8 - 1 - p;
+    const int i = cap / 8 - 1 - p;
     const int u = 8 * i + 7 - r - cc;
     float v = 0.f;
     if (u >= 0 && u < k_len) v = kc[u];
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(256) toeplitz_table_kernel(const float* __rest
 
 struct ToepParams {
   const __nv_bfloat16* E;  // table base
-  int L;                   // padded length (multiple of 128, <= kToepMaxL)
+  int L;                   // padded length (multiple of 128, <= cap)
+  int cap;                 // table built for reads up to cap tokens
   int n_rt;                // ceil(B / 128)
   int n_items;             // 256 * n_rt
 };
@@ -126,7 +128,7 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      constexpr int kP = kToepMaxL / 8 + kTzZeroChunks;  // chunks per channel in the table
+      const int kP = p.cap / 8 + kTzZeroChunks;  // chunks per channel in the table
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
         const int c = o / p.n_rt, rt = o % p.n_rt;
         const __nv_bfloat16* e_ch = p.E + (size_t)c * kP * 64;
@@ -139,9 +141,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
             mbar_arrive_expect_tx(afull(stage), kTzBox + kTzWin);
             const uint32_t dst = a_base + stage * kTzStage;
             tma_load_3d(dst, &tmV, afull(stage), kc * 64, c, rt * 128);
-            // window: core matrices i = q, q-1, ..., q-39 (table position p = kToepMaxL/8 - 1 - i)
+            // window: core matrices i = q, q-1, ..., q-39 (table position p = cap/8 - 1 - i)
             const int q = q0 - 8 * kc;
-            bulk_load_1d(dst + kTzBox, e_ch + (size_t)(kToepMaxL / 8 - 1 - q) * 64, kTzWin, afull(stage));
+            bulk_load_1d(dst + kTzBox, e_ch + (size_t)(p.cap / 8 - 1 - q) * 64, kTzWin, afull(stage));
             if (++stage == kTzAStages) {
               stage = 0;
               phase ^= 1;
@@ -284,78 +286,26 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
   }
 }
 
-__device__ __forceinline__ void unpack8b(const uint4 v, float (&f)[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// causal 3-tap depthwise conv of 8 consecutive tokens: out[t] = w0 z[t-2] + w1 z[t-1] + w2 z[t] + b
-__device__ __forceinline__ void sconv8(const __nv_bfloat16* __restrict__ row, int t0, const float* __restrict__ w,
-                                       float bias, float (&out)[8]) {
-  float z[10], cur[8];
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(row + t0)), cur);
-  z[0] = t0 >= 2 ? __bfloat162float(row[t0 - 2]) : 0.f;
-  z[1] = t0 >= 1 ? __bfloat162float(row[t0 - 1]) : 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) z[2 + i] = cur[i];
-  const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) out[i] = fmaf(w0, z[i], fmaf(w1, z[i + 1], fmaf(w2, z[i + 2], bias)));
-}
-
-// z [B,768,L] -> vv = sc(v)*sc(x1) and gate = sc(x0), both bf16 [B,256,L]; 8 tokens per thread
-__global__ void __launch_bounds__(256) shortconv_gate_kernel(const __nv_bfloat16* __restrict__ z,
-                                                             const float* __restrict__ sw, const float* __restrict__ sb,
-                                                             int B, int L, __nv_bfloat16* __restrict__ vv,
-                                                             __nv_bfloat16* __restrict__ gate) {
-  const int per_row = L / 8;
-  const size_t total = (size_t)B * 256 * per_row;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int g8 = (int)(idx % per_row);
-    const size_t bc = idx / per_row;
-    const int c = (int)(bc % 256);
-    const size_t b = bc / 256;
-    const int t0 = g8 * 8;
-    const __nv_bfloat16* zb = z + b * 768 * L;
-    float x0[8], x1[8], v[8];
-    sconv8(zb + (size_t)c * L, t0, sw + c * 3, __ldg(sb + c), x0);
-    sconv8(zb + (size_t)(256 + c) * L, t0, sw + (256 + c) * 3, __ldg(sb + 256 + c), x1);
-    sconv8(zb + (size_t)(512 + c) * L, t0, sw + (512 + c) * 3, __ldg(sb + 512 + c), v);
-    const size_t off = (b * 256 + c) * L + t0;
-    *reinterpret_cast<uint4*>(vv + off) = make_uint4(pack2(v[0] * x1[0], v[1] * x1[1]), pack2(v[2] * x1[2], v[3] * x1[3]),
-                                                     pack2(v[4] * x1[4], v[5] * x1[5]), pack2(v[6] * x1[6], v[7] * x1[7]));
-    *reinterpret_cast<uint4*>(gate + off) = make_uint4(pack2(x0[0], x0[1]), pack2(x0[2], x0[3]), pack2(x0[4], x0[5]),
-                                                       pack2(x0[6], x0[7]));
-  }
-}
-
-
-int launch_toeplitz_table(dcb200_ctx* ctx, const float* k, int k_stride, int k_len, const float* D, __nv_bfloat16* E) {
+int launch_toeplitz_table(dcb200_ctx* ctx, const float* k, int k_stride, int k_len, const float* D, int cap,
+                          __nv_bfloat16* E) {
   dim3 grid(8, 256);
-  toeplitz_table_kernel<<<grid, 256, 0, ctx->stream>>>(k, k_stride, k_len, D, E);
+  toeplitz_table_kernel<<<grid, 256, 0, ctx->stream>>>(k, k_stride, k_len, D, cap, E);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }
 
-size_t toeplitz_table_bytes() { return (size_t)256 * (kToepMaxL / 8 + kTzZeroChunks) * 128; }
+size_t toeplitz_table_bytes(int cap) { return (size_t)256 * (cap / 8 + kTzZeroChunks) * 128; }
 
-int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, const CUtensorMap& tm_vv, const CUtensorMap& tm_gate,
-                         const CUtensorMap& tm_y, int B, int L) {
-  if (L % 128 != 0 || L > kToepMaxL || L <= 0) {
-    set_error("toeplitz conv: L=%d must be a multiple of 128 and <= %d", L, kToepMaxL);
+int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, int cap, const CUtensorMap& tm_vv,
+                         const CUtensorMap& tm_gate, const CUtensorMap& tm_y, int B, int L) {
+  if (L % 128 != 0 || L > cap || L <= 0) {
+    set_error("toeplitz conv: L=%d must be a multiple of 128 and <= %d", L, cap);
     return DCB200_EINVAL;
   }
   ToepParams p;
   p.E = E;
   p.L = L;
+  p.cap = cap;
   p.n_rt = (B + 127) / 128;
   p.n_items = 256 * p.n_rt;
   const size_t want = (size_t)kTzAStages * kTzStage + (size_t)kTzGSlots * kTzBox + 1024 + 512;
@@ -367,18 +317,6 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, const CUtensor
   const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   ProfScope prof(ctx, K_TOEP);
   toeplitz_kernel<<<grid, kTzThreads, want, ctx->stream>>>(tm_vv, tm_gate, tm_y, p);
-  DCB_LAUNCH_CHECK(ctx);
-  return DCB200_OK;
-}
-
-int launch_shortconv_gate(dcb200_ctx* ctx, const __nv_bfloat16* z, const float* sw, const float* sb, int B, int L,
-                          __nv_bfloat16* vv, __nv_bfloat16* gate) {
-  const size_t total = (size_t)B * 256 * (L / 8);
-  size_t blocks = (total + 255) / 256;
-  const size_t cap = (size_t)ctx->sm_count * 8 * 8;
-  if (blocks > cap) blocks = cap;
-  ProfScope prof(ctx, K_SCONV);
-  shortconv_gate_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(z, sw, sb, B, L, vv, gate);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }

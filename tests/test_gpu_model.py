@@ -174,6 +174,21 @@ def test_forward_long_read(ref, gpu, B, L, conv_kind):
     close(f"logits L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
 
 
+@pytest.mark.parametrize("B,L", [(2, 12032), (1, 32768)])
+def test_forward_very_long_read(ref, gpu, B, L):
+    """BASELINE config 4 (16-32 kb reads): the Toeplitz long convolution covers the model's whole 32768-token range."""
+    rng = np.random.default_rng(13)
+    ids, q = make_batch(rng, B, L)
+    with torch.no_grad():
+        want = ref(ids, q)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    close(f"logits L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    lab_got = got[..., 1] > got[..., 0]
+    lab_want = want[..., 1] > want[..., 0]
+    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
+    assert torch.equal(lab_got[decided], lab_want[decided])
+
+
 def test_forward_arbitrary_length_is_right_filled(ref, gpu):
     # reference API accepts any [B, L]; rows are right-filled to the 128-token tile (causal => inert)
     rng = np.random.default_rng(9)
