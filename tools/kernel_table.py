@@ -16,5 +16,9 @@ for line in src:
     for k, v in d["kernels"].items():
         print(f"  {k:16s} {v['ms_total']:9.2f} ms  n={v['launches']:5d}  share {v['share']:.3f}  "
               f"{v.get('achieved', 0):9.1f} {v.get('unit', ''):8s} frac {v.get('frac', 0):.3f}")
+    if d.get("hyena_layer"):
+        print("  hyena_layer", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in d["hyena_layer"].items() if k != "note"})
+    if d.get("roofline"):
+        print("  roofline", d["roofline"])
     if "cpu_baseline" in d:
         print("  cpu_baseline", d["cpu_baseline"])
