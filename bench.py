@@ -319,10 +319,20 @@ def run_ours(args, rank, local, world):
                  "note": "dense GEMM FLOPs only (the long convolution's Toeplitz MMAs are extra work, not counted)"}
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_final_traffic.json")
+    if dom and os.path.exists(tpath):
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture, scaled
+        # from the profiled batch to this run's average launch (bytes per token x tokens per launch)
+        ent = json.load(open(tpath))["kernels"].get(dom)
+        if ent:
+            launches_per_step = kernels[dom]["launches"] / max(1, args.steps)
+            tokens_per_launch = padded_tokens * (N_LAYERS if dom in PER_LAYER else 1) / max(1.0, launches_per_step)
+            traffic = ent["dram_bytes_per_token"] * tokens_per_launch
     if dom:
         k = kernels[dom]
         roofline = {"kernel": dom, "bound": k.get("bound"), "achieved": k.get("achieved"), "peak": k.get("peak"),
-                    "unit": k.get("unit"), "frac": k.get("frac"), "traffic": None, "peak_source": peaks["source"],
+                    "unit": k.get("unit"), "frac": k.get("frac"), "traffic": traffic, "peak_source": peaks["source"],
                     "avg_launch_ms": k["ms_total"] / max(1, k["launches"])}
 
     if rank != 0:
