@@ -395,37 +395,49 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
         tr(440 + j);
       }
       // ---- final: x = acc2 + b2 (+ residual, already in acc2) -> h_out ; LayerNorm -> u ------------------------------
-      // Global stores are plain coalesced st.global: each warp transposes its own 32 rows through a private 4 KB
-      // scratch (row-owner writes, 4 rows x 128 B reads), so the tile's tail never waits on the TMA queue.
+      // My 64 columns of x stay in registers from here on, so acc2 goes back to the MMA warp after ~1 k cycles (fc2(0) of
+      // the next tile only waits for that and for GELU(0)).  Global stores are plain coalesced st.global: each warp
+      // transposes its own 32 rows through a private 4 KB scratch (row-owner writes, 4 rows x 128 B reads).
       tr(500);
       mbar_wait(bar(T2_FULL), n & 1);
       tr(501);
       tc_fence_after();
+      uint32_t v2[32];
+      const int colA = part * 64;
+      tmem_ld32(tmem_base + lane_off + colA, v);
+      tmem_ld32(tmem_base + lane_off + colA + 32, v2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(t2_empty);  // acc2 drained
       float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float xa = __uint_as_float(v[i]) + p.b2[colA + i];
+        const float xb = __uint_as_float(v2[i]) + p.b2[colA + 32 + i];
+        sum += xa + xb;
+        sq = fmaf(xa, xa, fmaf(xb, xb, sq));
+        v[i] = __float_as_uint(xa);
+        v2[i] = __float_as_uint(xb);
+      }
+      // row statistics (sum, sum of squares) over the four column parts, in a fixed order: (p0 + p1) + (p2 + p3)
+      float2* st2 = stats + (part >> 1) * 128 + row;
+      if (part & 1) *st2 = make_float2(sum, sq);
+      bar_sync(6 + quad, 128);  // the four warps that share these 32 rows
+      if (!(part & 1)) {
+        const float2 o = *st2;
+        *st2 = make_float2(sum + o.x, sq + o.y);
+      }
+      tr(540);
       const uint32_t scratch = my_slot + quad * 4096;
       const uint32_t own = scratch + lane * 128;                       // my row, row-owner layout
       const int trow = lane >> 3, tchunk = lane & 7;                     // T layout: row 4 i + trow, 16-byte chunk tchunk
       const size_t grow0 = (size_t)tok0 + quad * 32;
 #pragma unroll
       for (int st = 0; st < 2; ++st) {
-        const int col0 = part * 64 + st * 32;
-        tmem_ld32(tmem_base + lane_off + col0, v);
-        tmem_ld_wait();
+        const uint32_t (&x)[32] = st ? v2 : v;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float x0 = __uint_as_float(v[4 * q]) + p.b2[col0 + 4 * q];
-          const float x1 = __uint_as_float(v[4 * q + 1]) + p.b2[col0 + 4 * q + 1];
-          const float x2 = __uint_as_float(v[4 * q + 2]) + p.b2[col0 + 4 * q + 2];
-          const float x3 = __uint_as_float(v[4 * q + 3]) + p.b2[col0 + 4 * q + 3];
-          sum += (x0 + x1) + (x2 + x3);
-          sq = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq))));
-          v[4 * q] = __float_as_uint(x0);
-          v[4 * q + 1] = __float_as_uint(x1);
-          v[4 * q + 2] = __float_as_uint(x2);
-          v[4 * q + 3] = __float_as_uint(x3);
-          sts128(own + (((uint32_t)q ^ sw) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        tmem_st32(tmem_base + lane_off + col0, v);  // x stays in TMEM for the normalisation pass
+        for (int q = 0; q < 8; ++q) sts128(own + (((uint32_t)q ^ sw) << 4), x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -433,21 +445,11 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
           uint32_t w[4];
           lds128(scratch + r * 128 + (((uint32_t)tchunk ^ (uint32_t)(r & 7)) << 4), w);
           if (grow0 + r < (size_t)p.T)
-            *reinterpret_cast<uint4*>(p.h_out + (grow0 + r) * 256 + col0 + tchunk * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(p.h_out + (grow0 + r) * 256 + colA + st * 32 + tchunk * 4) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         __syncwarp();
       }
-      tr(540);
-      // row statistics (sum, sum of squares) over the four column parts, in a fixed order: (p0 + p1) + (p2 + p3)
-      float2* st2 = stats + (part >> 1) * 128 + row;
-      if (part & 1) *st2 = make_float2(sum, sq);
-      tmem_st_wait();
-      bar_sync(6 + quad, 128);  // the four warps that share these 32 rows
-      if (!(part & 1)) {
-        const float2 o = *st2;
-        *st2 = make_float2(sum + o.x, sq + o.y);
-      }
-      bar_sync(6 + quad, 128);
+      bar_sync(6 + quad, 128);  // pair sums of all four parts are in place
       tr(551);
       float2 sa = stats[row];
       {
@@ -458,31 +460,27 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       const float mean = sa.x * (1.0f / 256.0f);
       const float rstd = rsqrtf(fmaxf(sa.y * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
       {  // u: my 64 bf16 columns (128 B per row)
-        const int col0 = part * 64;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tmem_ld32(tmem_base + lane_off + col0 + c * 32, v);
-          tmem_ld_wait();
+          const uint32_t (&x)[32] = c ? v2 : v;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int col = col0 + c * 32 + q * 8;
+            const int col = colA + c * 32 + q * 8;
             float y[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(v[q * 8 + i]) - mean) * rstd, p.ln_g[col + i], p.ln_b[col + i]);
+            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, p.ln_g[col + i], p.ln_b[col + i]);
             sts128(own + (((uint32_t)(c * 4 + q) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
                    pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
           }
         }
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(t2_empty);  // acc2 fully drained: fc2(0) of the next tile may overwrite it
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + trow;
           uint32_t w[4];
           lds128(scratch + r * 128 + (((uint32_t)tchunk ^ (uint32_t)(r & 7)) << 4), w);
           if (grow0 + r < (size_t)p.T)
-            *reinterpret_cast<uint4*>(p.u_out + (grow0 + r) * 256 + col0 + tchunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(p.u_out + (grow0 + r) * 256 + colA + tchunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       tr(560);
