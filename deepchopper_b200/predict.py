@@ -33,7 +33,7 @@ class Batch:
     Lrow: int             # row stride, multiple of 128
 
 
-def plan_batches(lens: np.ndarray, token_budget: int = 512 * 1024, max_rows: int = 4096,
+def plan_batches(lens: np.ndarray, token_budget: int = 1024 * 1024, max_rows: int = 8192,
                  sort: bool = True) -> List[Batch]:
     """Length-bucketed batches of ~token_budget padded tokens.  ``sort=False`` keeps FASTQ order
     (the reference's own batching when combined with a fixed ``max_rows``)."""
