@@ -291,6 +291,8 @@ def run_ours(args, rank, local, world):
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
     e2e_value = bases_all * e2e_steps / e2e_s
+    h2d = int(sum_over_ranks(h2d, world, dev))  # whole-job bytes per step, like `value`
+    d2h = int(sum_over_ranks(d2h, world, dev))
 
     # ---- per-kernel roofline (CUDA events on the launching stream, timed region above) ---------------
     kernels = {}
