@@ -121,6 +121,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
     prefetch_tmap(&tmW1);
     prefetch_tmap(&tmW2);
     prefetch_tmap(&tmHin);
+    prefetch_tmap(&tmHout);
+    prefetch_tmap(&tmU);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar(A_FULL), 1);
@@ -429,27 +431,27 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
         *st2 = make_float2(sum + o.x, sq + o.y);
       }
       tr(540);
-      const uint32_t scratch = my_slot + quad * 4096;
-      const uint32_t own = scratch + lane * 128;                       // my row, row-owner layout
-      const int trow = lane >> 3, tchunk = lane & 7;                     // T layout: row 4 i + trow, 16-byte chunk tchunk
-      const size_t grow0 = (size_t)tok0 + quad * 32;
+      // Three boxes (h_out columns [64p, +32), [64p+32, +32) as fp32, u columns [64p, +64) as bf16; 16 KB each) go
+      // through my part's slot to TMA stores: the LSU store path sustains only ~24 B/clk per SM here (its queue of
+      // outstanding L2 writes is latency bound), TMA is not.  The slot is rewritten once the previous store has read it.
+      const uint32_t own = my_slot + row * 128;  // my row of the 128-row box, 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
       for (int st = 0; st < 2; ++st) {
         const uint32_t (&x)[32] = st ? v2 : v;
+        if (st == 1) bar_sync(2 + part, 128);  // (the storer arrives after the first store has read the slot)
 #pragma unroll
         for (int q = 0; q < 8; ++q) sts128(own + (((uint32_t)q ^ sw) << 4), x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + trow;
-          uint32_t w[4];
-          lds128(scratch + r * 128 + (((uint32_t)tchunk ^ (uint32_t)(r & 7)) << 4), w);
-          if (grow0 + r < (size_t)p.T)
-            *reinterpret_cast<uint4*>(p.h_out + (grow0 + r) * 256 + colA + st * 32 + tchunk * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+        fence_proxy_async();
+        bar_sync(2 + part, 128);
+        if (storer) {
+          tma_store_2d(&tmHout, my_slot, colA + st * 32, tok0);
+          bulk_commit();
         }
-        __syncwarp();
+        if (st == 0) {
+          bar_sync(6 + quad, 128);  // pair sums of all four parts are in place
+        }
+        if (storer) bulk_wait_read<0>();
       }
-      bar_sync(6 + quad, 128);  // pair sums of all four parts are in place
       tr(551);
       float2 sa = stats[row];
       {
@@ -459,33 +461,40 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
       }
       const float mean = sa.x * (1.0f / 256.0f);
       const float rstd = rsqrtf(fmaxf(sa.y * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
-      {  // u: my 64 bf16 columns (128 B per row)
+      {  // u: my 64 bf16 columns (128 B per row), normalised in registers while the second h_out store drains
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const uint32_t (&x)[32] = c ? v2 : v;
+          uint32_t (&x)[32] = c ? v2 : v;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = colA + c * 32 + q * 8;
             float y[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, p.ln_g[col + i], p.ln_b[col + i]);
-            sts128(own + (((uint32_t)(c * 4 + q) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
-                   pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[q * 4 + i] = pack_bf16(y[2 * i], y[2 * i + 1]);  // (in place: index q*4+i <= q*8+2i)
           }
         }
-        __syncwarp();
+        bar_sync(2 + part, 128);  // slot free again
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + trow;
-          uint32_t w[4];
-          lds128(scratch + r * 128 + (((uint32_t)tchunk ^ (uint32_t)(r & 7)) << 4), w);
-          if (grow0 + r < (size_t)p.T)
-            *reinterpret_cast<uint4*>(p.u_out + (grow0 + r) * 256 + colA + tchunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t (&x)[32] = c ? v2 : v;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(own + (((uint32_t)(c * 4 + q) ^ sw) << 4), x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+        }
+        fence_proxy_async();
+        bar_sync(2 + part, 128);
+        if (storer) {
+          tma_store_2d(&tmU, my_slot, colA, tok0);
+          bulk_commit();
+          bulk_wait_read<0>();
         }
       }
       tr(560);
-      bar_sync(1, 512);  // every warp is done with its scratch (G halves / D slots): the next tile may reuse them
+      bar_sync(1, 512);  // every store has read its slot (G halves / D slots): the next tile may reuse them
     }
+    if (storer) bulk_wait<0>();
   }
 
   tc_fence_before();
