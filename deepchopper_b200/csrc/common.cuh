@@ -83,6 +83,20 @@ struct dcb200_ctx {
   // named workspaces (activations, staging), grow-only
   std::map<std::string, dcb::DevBuf> ws;
   dcb::DevBuf& buf(const char* name) { return ws[name]; }
+  // kernels whose dynamic shared-memory limit has been raised on THIS device (the attribute is per device, and one
+  // process may hold contexts on several)
+  std::map<const void*, size_t> smem_attr;
+  int ensure_smem(const void* func, size_t bytes) {
+    auto it = smem_attr.find(func);
+    if (it != smem_attr.end() && it->second >= bytes) return DCB200_OK;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      dcb::set_error("cudaFuncSetAttribute(max dynamic smem = %zu) failed: %s", bytes, cudaGetErrorString(e));
+      return DCB200_ECUDA;
+    }
+    smem_attr[func] = bytes;
+    return DCB200_OK;
+  }
   // optional per-kernel CUDA-event timing (bench.py's roofline numbers)
   bool profiling = false;
   std::vector<dcb::ProfRec> prof_recs;

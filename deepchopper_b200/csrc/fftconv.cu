@@ -295,16 +295,12 @@ static int conv_threads(int N) {
 }
 
 int launch_fftconv(dcb200_ctx* ctx, const ConvParams& p) {
-  static size_t configured = 0;
   const size_t smem = conv_smem_bytes(p.plan.N, p.L);
   if (smem > 227 * 1024) {
     set_error("fftconv: L=%d needs %zu bytes of shared memory (long-read path not built yet)", p.L, smem);
     return DCB200_EINVAL;
   }
-  if (smem > configured) {
-    DCB_CUDA(cudaFuncSetAttribute(fftconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = 227 * 1024;
-  }
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&fftconv_kernel), 227 * 1024));
   dim3 grid((p.B + 1) / 2, 256);
   ProfScope prof(ctx, K_CONV);
   fftconv_kernel<<<grid, conv_threads(p.plan.N), smem, ctx->stream>>>(p);
@@ -314,12 +310,8 @@ int launch_fftconv(dcb200_ctx* ctx, const ConvParams& p) {
 
 int launch_filter_spectrum(dcb200_ctx* ctx, const float* k, int k_stride, int k_len, const float* D, const FftPlan& plan,
                            const float2* tw, float2* KF) {
-  static bool configured = false;
   const size_t smem = (size_t)(plan.N + plan.N / 16) * 8;
-  if (!configured) {
-    DCB_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = true;
-  }
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&filter_spectrum_kernel), 227 * 1024));
   filter_spectrum_kernel<<<256, conv_threads(plan.N), smem, ctx->stream>>>(k, k_stride, k_len, D, plan, tw, KF);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;

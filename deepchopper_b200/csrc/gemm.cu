@@ -172,13 +172,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_after();
             const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
             const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t adesc = Tr::A_MN ? make_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                              : make_desc_sw128(a_addr + k * 32, 16, 1024);
-              const uint64_t bdesc = make_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) ? 1u : 0u);
-            }
+            // K-major tiles advance 32 B per K = 16 slice; the MN-major A tile (out_proj) 2 KB per slice
+            const uint64_t adesc0 = Tr::A_MN ? make_desc_sw128(a_addr, 8192, 1024) : make_desc_sw128(a_addr, 16, 1024);
+            umma_bf16_x4<1>(d_tmem, adesc0, Tr::A_MN ? 128 : 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kc ? 1u : 0u);
             umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
             if (++stage == kStages) {
               stage = 0;
@@ -481,12 +477,8 @@ template <int MODE> static size_t smem_bytes() {
 }
 
 template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
-  static bool configured = false;
   const size_t smem = smem_bytes<MODE>();
-  if (!configured) {
-    DCB_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&gemm_kernel<MODE>), smem));
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
   static const int kinds[4] = {K_INPROJ, K_OUTPROJ, K_HEAD1, K_HEAD2};
   ProfScope prof(ctx, kinds[MODE]);

@@ -4,7 +4,8 @@
 // replacing gemm_kernel<INPROJ> + shortconv_gate_kernel: z ([B,768,L] bf16, 1.5 KB per token written and read back)
 // never exists.  HBM traffic per token: read u (512 B), write vv + gate (1 KB).
 //
-// One persistent CTA per SM.  A work unit is (128-token tile, 128-channel group): three tcgen05 MMA series
+// One persistent CTA per SM (a CTA-pair variant with M = 256 MMAs measured 5 % slower: the kernel is bound by waits
+// around the MMA series, not by the MMA rate).  A work unit is (128-token tile, 128-channel group): three tcgen05 MMA series
 //   x1 = W_in[256+c..] . u^T ,  v = W_in[512+c..] . u^T ,  x0 = W_in[c..] . u^T        (M = 128 channels, K = 256)
 // with N = 144 tokens: the tile plus the 16 tokens before it, so the causal 3-tap convolution (which needs z[t-1],
 // z[t-2]) has its halo in the same accumulator and tiles stay independent.  The accumulator rows are channels, so an
@@ -48,13 +49,16 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& 
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
 
-// causal 3-tap conv of 32 consecutive tokens given z[t-2], z[t-1] (h0, h1) and z[0..31]; out may alias nothing
-__device__ __forceinline__ void sconv32(const float (&z)[32], float h0, float h1, float w0, float w1, float w2, float cb,
-                                        float (&out)[32]) {
-  out[0] = fmaf(w0, h0, fmaf(w1, h1, fmaf(w2, z[0], cb)));
-  out[1] = fmaf(w0, h1, fmaf(w1, z[0], fmaf(w2, z[1], cb)));
+// Causal 3-tap conv of 32 consecutive tokens, IN PLACE on the raw accumulator values r[0..31] (h0, h1 = raw values of
+// the two tokens before).  The in_linear bias b is folded into the constant: w0 (a0+b) + w1 (a1+b) + w2 (a2+b) + cb =
+// w0 a0 + w1 a1 + w2 a2 + (cb + b (w0+w1+w2)); descending order keeps the taps it still needs intact.
+__device__ __forceinline__ void sconv32_inplace(uint32_t (&r)[32], uint32_t h0, uint32_t h1, float w0, float w1, float w2,
+                                                float cbf) {
 #pragma unroll
-  for (int i = 2; i < 32; ++i) out[i] = fmaf(w0, z[i - 2], fmaf(w1, z[i - 1], fmaf(w2, z[i], cb)));
+  for (int i = 31; i >= 2; --i)
+    r[i] = __float_as_uint(fmaf(w0, __uint_as_float(r[i - 2]), fmaf(w1, __uint_as_float(r[i - 1]), fmaf(w2, __uint_as_float(r[i]), cbf))));
+  r[1] = __float_as_uint(fmaf(w0, __uint_as_float(h1), fmaf(w1, __uint_as_float(r[0]), fmaf(w2, __uint_as_float(r[1]), cbf))));
+  r[0] = __float_as_uint(fmaf(w0, __uint_as_float(h0), fmaf(w1, __uint_as_float(h1), fmaf(w2, __uint_as_float(r[0]), cbf))));
 }
 
 }  // namespace
@@ -167,10 +171,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
               tc_fence_after();
               const uint32_t a_addr = w_base + stage * kWBox;
               const uint32_t b_addr = u_base + kb * kUBox;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d, make_desc_sw128(a_addr + k * 32, 16, 1024), make_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
-                          (kb | k) ? 1u : 0u);
+              umma_bf16_x4<1>(d, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kb ? 1u : 0u);
               umma_commit(bar(W_EMPTY + stage));
               if (g == 1 && s == 2) umma_commit(bar(U_EMPTY + kb));  // last series of the tile: u box kb may be refilled
               if (++stage == kWStages) {
@@ -202,8 +203,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         {
           const float* c1 = cst + (256 + ch) * 5;
           const float* cv = cst + (512 + ch) * 5;
-          const float b1 = c1[0], w10 = c1[1], w11 = c1[2], w12 = c1[3], cb1 = c1[4];
-          const float bv = cv[0], wv0 = cv[1], wv1 = cv[2], wv2 = cv[3], cbv = cv[4];
+          const float b1 = c1[0], w10 = c1[1], w11 = c1[2], w12 = c1[3], cb1 = fmaf(c1[0], (c1[1] + c1[2]) + c1[3], c1[4]);
+          const float bv = cv[0], wv0 = cv[1], wv1 = cv[2], wv2 = cv[3], cbv = fmaf(cv[0], (cv[1] + cv[2]) + cv[3], cv[4]);
           mbar_wait(bar(R_FULL + 0), use & 1);
           mbar_wait(bar(R_FULL + 1), use & 1);
           tc_fence_after();
@@ -221,22 +222,23 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             tmem_ld32(t_v + 32 * sub, rb);
             tmem_ld2(t_v + 32 * sub - 2, hb0, hb1);
             tmem_ld_wait();
-            float z[32], c1o[32], cvo[32];
+            // at the start of a read the conv input is zero-padded: make the halo's (raw + bias) vanish
             const bool zero_halo = row_start && half == 0 && sub == 0;
+            if (zero_halo) {
+              ha0 = ha1 = __float_as_uint(-b1);
+              hb0 = hb1 = __float_as_uint(-bv);
+            }
+            sconv32_inplace(ra, ha0, ha1, w10, w11, w12, cb1);
+            sconv32_inplace(rb, hb0, hb1, wv0, wv1, wv2, cbv);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(ra[i]) + b1;
-            sconv32(z, zero_halo ? 0.f : __uint_as_float(ha0) + b1, zero_halo ? 0.f : __uint_as_float(ha1) + b1, w10, w11, w12, cb1,
-                    c1o);
+            for (int q = 0; q < 4; ++q) {
+              uint32_t o[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(rb[i]) + bv;
-            sconv32(z, zero_halo ? 0.f : __uint_as_float(hb0) + bv, zero_halo ? 0.f : __uint_as_float(hb1) + bv, wv0, wv1, wv2, cbv,
-                    cvo);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4), pack_bf16(c1o[8 * q] * cvo[8 * q], c1o[8 * q + 1] * cvo[8 * q + 1]),
-                     pack_bf16(c1o[8 * q + 2] * cvo[8 * q + 2], c1o[8 * q + 3] * cvo[8 * q + 3]),
-                     pack_bf16(c1o[8 * q + 4] * cvo[8 * q + 4], c1o[8 * q + 5] * cvo[8 * q + 5]),
-                     pack_bf16(c1o[8 * q + 6] * cvo[8 * q + 6], c1o[8 * q + 7] * cvo[8 * q + 7]));
+              for (int i = 0; i < 4; ++i)
+                o[i] = pack_bf16(__uint_as_float(ra[8 * q + 2 * i]) * __uint_as_float(rb[8 * q + 2 * i]),
+                                 __uint_as_float(ra[8 * q + 2 * i + 1]) * __uint_as_float(rb[8 * q + 2 * i + 1]));
+              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4), o[0], o[1], o[2], o[3]);
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -254,7 +256,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         // ---- G: sc(x0) ---------------------------------------------------------------------------------------------
         {
           const float* c0 = cst + ch * 5;
-          const float b0 = c0[0], w0 = c0[1], w1 = c0[2], w2 = c0[3], cb0 = c0[4];
+          const float b0 = c0[0], w0 = c0[1], w1 = c0[2], w2 = c0[3], cb0 = fmaf(c0[0], (c0[1] + c0[2]) + c0[3], c0[4]);
           mbar_wait(bar(R_FULL + 2), use & 1);
           tc_fence_after();
           const uint32_t t_x0 = tmem_base + lane_off + 2 * kRegionStride + kHalo + 64 * half;
@@ -267,16 +269,15 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             tmem_ld32(t_x0 + 32 * sub, ra);
             tmem_ld2(t_x0 + 32 * sub - 2, ha0, ha1);
             tmem_ld_wait();
-            float z[32], co[32];
-            const bool zero_halo = row_start && half == 0 && sub == 0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(ra[i]) + b0;
-            sconv32(z, zero_halo ? 0.f : __uint_as_float(ha0) + b0, zero_halo ? 0.f : __uint_as_float(ha1) + b0, w0, w1, w2, cb0, co);
+            if (row_start && half == 0 && sub == 0) ha0 = ha1 = __float_as_uint(-b0);
+            sconv32_inplace(ra, ha0, ha1, w0, w1, w2, cb0);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4), pack_bf16(co[8 * q], co[8 * q + 1]),
-                     pack_bf16(co[8 * q + 2], co[8 * q + 3]), pack_bf16(co[8 * q + 4], co[8 * q + 5]),
-                     pack_bf16(co[8 * q + 6], co[8 * q + 7]));
+              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4),
+                     pack_bf16(__uint_as_float(ra[8 * q]), __uint_as_float(ra[8 * q + 1])),
+                     pack_bf16(__uint_as_float(ra[8 * q + 2]), __uint_as_float(ra[8 * q + 3])),
+                     pack_bf16(__uint_as_float(ra[8 * q + 4]), __uint_as_float(ra[8 * q + 5])),
+                     pack_bf16(__uint_as_float(ra[8 * q + 6]), __uint_as_float(ra[8 * q + 7])));
           }
           tc_fence_before();
           __syncwarp();
@@ -304,11 +305,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorMap& tm_w, const CUtensorMap& tm_vv,
                        const CUtensorMap& tm_gate, const InprojParams& p) {
   const size_t smem = 4 * kUBox + kWStages * kWBox + 4 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    DCB_CUDA(cudaFuncSetAttribute(inproj_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&inproj_conv_kernel), smem));
   const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
   ProfScope prof(ctx, K_INPROJ);
   inproj_conv_kernel<<<grid, kThreads, smem, ctx->stream>>>(tm_u, tm_w, tm_vv, tm_gate, p);

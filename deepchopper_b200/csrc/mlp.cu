@@ -67,21 +67,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Optional timeline trace (DCB200_TRACE=1): (tag, SM clock) records of one MMA thread / one epilogue warp / one producer,
-// read back with dcb200_ctx_read_workspace("trace").  Costs one predictable branch when off.
-constexpr int kTraceCap = 4096;
-struct Tracer {
-  long long* buf;
-  int n;
-  __device__ __forceinline__ void operator()(int tag) {
-    if (buf && n < kTraceCap) {
-      buf[2 * n] = tag;
-      buf[2 * n + 1] = clock64();
-      ++n;
-    }
-  }
-};
-
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -228,10 +213,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
             tc_fence_after();
             const uint32_t a_addr = a_base + kb * kUnitBytes;
             const uint32_t b_addr = w_base + slot * kUnitBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_2sm(d, make_desc_sw128(a_addr + k * 32, 16, 1024), make_desc_sw128(b_addr + k * 32, 16, 1024), idesc2,
-                            (kb | k) ? 1u : 0u);
+            umma_bf16_x4<2>(d, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc2, kb ? 1u : 0u);
             umma_commit_2sm(bar(W_EMPTY + slot), 3);
             advance();
           }
@@ -251,10 +233,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
             tc_fence_after();
             const uint32_t a_addr = g_base + kb * kUnitBytes;
             const uint32_t b_addr = w_base + slot * kUnitBytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_2sm(tmem_base, make_desc_sw128(a_addr + k * 32, 16, 1024), make_desc_sw128(b_addr + k * 32, 16, 1024),
-                            idesc2, (j | kb | k) ? 1u : 0u);
+            umma_bf16_x4<2>(tmem_base, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc2,
+                            (j | kb) ? 1u : 0u);
             umma_commit_2sm(bar(W_EMPTY + slot), 3);
             advance();
           }
@@ -509,11 +489,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUte
 int launch_mlp(dcb200_ctx* ctx, const CUtensorMap& tm_m, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                const CUtensorMap& tm_hin, const CUtensorMap& tm_hout, const CUtensorMap& tm_u, const MlpParams& p) {
   const size_t smem = kABytes + kSlots * kUnitBytes + kGBytes + 2 * kUnitBytes + 2 * 128 * 8 + 40 * 8;
-  static bool configured = false;
-  if (!configured) {
-    DCB_CUDA(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&mlp_kernel), smem));
   int clusters = ctx->sm_count / 2;
   if (p.num_pairs < clusters) clusters = p.num_pairs;
   cudaLaunchConfig_t cfg;

@@ -500,7 +500,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       memcpy(mp.ln_g, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_g.data() : w->h_lnf_g.data(), sizeof(mp.ln_g));
       memcpy(mp.ln_b, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_b.data() : w->h_lnf_b.data(), sizeof(mp.ln_b));
       mp.trace = nullptr;
-      if (l == 0 && getenv("DCB200_TRACE")) {
+      if (l == 0 && getenv("DCB200_TRACE") && !strcmp(getenv("DCB200_TRACE"), "mlp")) {
         DevBuf& bt = ctx->buf("trace");
         DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
         DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));

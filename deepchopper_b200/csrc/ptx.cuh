@@ -250,6 +250,44 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                : "memory");
 }
 
+// Four consecutive K = 16 MMAs of one 64-wide K block in ONE asm block: the descriptors advance by a constant number
+// of 16-byte units (2 = 32 bytes inside a 128B-swizzled K-major tile), the accumulate predicate is evaluated once.
+// The issuing thread is a single lane running dependent scalar code: rebuilding two 64-bit descriptors and a
+// predicate per MMA (~15 dependent instructions) made small-N MMAs issue-bound at ~200 cycles apiece.
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint64_t a0, uint32_t a_inc, uint64_t b0, uint32_t b_inc,
+                                             uint32_t idesc, uint32_t accumulate_first) {
+  const uint64_t a1 = a0 + a_inc, a2 = a0 + 2 * a_inc, a3 = a0 + 3 * a_inc;
+  const uint64_t b1 = b0 + b_inc, b2 = b0 + 2 * b_inc, b3 = b0 + 3 * b_inc;
+  if (kCtaGroup == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1;\n"
+        "setp.ne.b32 p0, %10, 0;\n"
+        "setp.eq.b32 p1, %10, %10;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %5, %9, p0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %6, %9, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %7, %9, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %8, %9, p1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1;\n"
+        "setp.ne.b32 p0, %10, 0;\n"
+        "setp.eq.b32 p1, %10, %10;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %5, %9, p0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %6, %9, p1;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %7, %9, p1;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %4, %8, %9, p1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  }
+}
+
 // ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: half the issue slots of scalar fp32) -------
 __device__ __forceinline__ uint64_t f2_pack(float a, float b) {
   uint64_t r;
@@ -307,4 +345,21 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 }
 
 }  // namespace ptx
+
+// Optional timeline trace (DCB200_TRACE=mlp|inproj): (tag, SM clock) records of one MMA thread / one epilogue warp / one producer,
+// read back with dcb200_ctx_read_workspace("trace").  Costs one predictable branch when off.
+constexpr int kTraceCap = 4096;
+struct Tracer {
+  long long* buf;
+  int n;
+  __device__ __forceinline__ void operator()(int tag) {
+    if (buf && n < kTraceCap) {
+      buf[2 * n] = tag;
+      buf[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+
+
 }  // namespace dcb

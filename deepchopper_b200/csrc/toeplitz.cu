@@ -173,12 +173,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
               mbar_wait(afull(stage), phase);
               tc_fence_after();
               const uint32_t a_addr = a_base + stage * kTzStage;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t adesc = make_desc_sw128(a_addr + k * 32, 16, 1024);
-                const uint64_t bdesc = make_desc_nosw(a_addr + kTzBox + k * 256, 128, 128);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, (i | hh | k) ? 1u : 0u);
-              }
+              // A: +32 B per K = 16 slice inside the swizzled tile; B: the window slides by two core matrices (256 B)
+              umma_bf16_x4<1>(d_tmem, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_nosw(a_addr + kTzBox, 128, 128), 16, idesc,
+                              (i | hh) ? 1u : 0u);
               umma_commit(aempty(stage));
               if (++stage == kTzAStages) {
                 stage = 0;
@@ -309,11 +306,7 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, int cap, const
   p.n_rt = (B + 127) / 128;
   p.n_items = 256 * p.n_rt;
   const size_t want = (size_t)kTzAStages * kTzStage + (size_t)kTzGSlots * kTzBox + 1024 + 512;
-  static bool configured = false;
-  if (!configured) {
-    DCB_CUDA(cudaFuncSetAttribute(toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-    configured = true;
-  }
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&toeplitz_kernel), want));
   const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   ProfScope prof(ctx, K_TOEP);
   toeplitz_kernel<<<grid, kTzThreads, want, ctx->stream>>>(tm_vv, tm_gate, tm_y, p);

@@ -52,9 +52,20 @@ def plan_batches(lens: np.ndarray, token_budget: int = 1024 * 1024, max_rows: in
                 break
             mx = m2
             j += 1
-        # the long-convolution kernel works on 128-row tiles of one channel: keep full tiles when the batch is large
+        # The long-convolution kernel's work items are (channel, 128-row tile): 256 x rows/128 items over 148 SMs.
+        # Full row tiles, and a multiple of 4 of them when the batch is large (256 x 4 k / 148 = 6.92 k waves: a 1 %
+        # tail instead of up to 13 %); the token budget is soft (<= 1.3 x).
         if sort and j - i > ROW_TILE and j < n:
-            j = i + (j - i) // ROW_TILE * ROW_TILE
+            rows = j - i
+            big = 4 * ROW_TILE
+            up = (rows // big + 1) * big
+            if rows >= 3 * ROW_TILE and i + up <= n and up <= max_rows:
+                lrow_up = (int(lens[order[i + up - 1]]) + 1 + ROW_TILE - 1) // ROW_TILE * ROW_TILE
+                if up * lrow_up <= 1.3 * token_budget:
+                    rows = up
+            if rows != up:
+                rows = rows // big * big if rows >= big else rows // ROW_TILE * ROW_TILE
+            j = i + rows
             mx = int(lens[order[j - 1]])
         lpad = mx + 1
         batches.append(Batch(order[i:j].copy(), lpad, (lpad + ROW_TILE - 1) // ROW_TILE * ROW_TILE))

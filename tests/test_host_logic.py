@@ -23,7 +23,8 @@ def test_plan_batches_covers_every_read_once():
     assert np.array_equal(np.sort(seen), np.arange(lens.size))
     for b in bs:
         assert b.Lpad == lens[b.rows].max() + 1 and b.Lrow % 128 == 0 and b.Lrow >= b.Lpad
-        assert b.rows.size == 1 or b.rows.size * b.Lrow <= 256 * 1024
+        # the token budget is soft: row counts are rounded to full 128-row tiles (x4 when large), at most 1.3 x budget
+        assert b.rows.size == 1 or b.rows.size * b.Lrow <= 1.3 * 256 * 1024
     # reference batching: FASTQ order, fixed rows
     fb = plan_batches(lens, token_budget=1 << 62, max_rows=12, sort=False)
     assert all(np.array_equal(b.rows, np.arange(i * 12, min(lens.size, (i + 1) * 12))) for i, b in enumerate(fb))

@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import torch
 
-os.environ["DCB200_TRACE"] = "1"
+os.environ["DCB200_TRACE"] = os.environ.get("DCB200_TRACE", "mlp")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepchopper_b200._native import check, lib  # noqa: E402
 from deepchopper_b200.init_weights import random_state_dict  # noqa: E402
