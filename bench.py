@@ -31,7 +31,8 @@ METRIC = "bases_per_sec_predict_smooth"
 UNIT = "bases/s"
 
 # algorithmic work per padded token (SURVEY §8d / DESIGN.md), used for the roofline figures
-FLOPS_PER_TOKEN = {"mlp": 2 * 2 * 256 * 1024,              # fused fc1 + GELU + fc2 + residual + LN
+FLOPS_PER_TOKEN = {"block": 2 * 256 * 256 + 2 * 2 * 256 * 1024,  # out_proj + LN2 + fc1 + GELU + fc2 + residual + LN, one kernel
+                   "mlp": 2 * 2 * 256 * 1024,              # (DCB200_BLOCK=split) fused fc1 + GELU + fc2 + residual + LN
                    "in_proj": 2 * 256 * 768,               # fused with the short conv + first gate (Toeplitz path)
                    "out_proj": 2 * 256 * 256,
                    "head1": 2 * 256 * 1024, "head2": 2 * (1024 * 1024 + 2 * 1024)}
@@ -43,11 +44,11 @@ BYTES_PER_TOKEN = {"hyena_conv": 768 * 2 + 256 * 2,        # FFT fallback: read 
 
 
 # kernels launched once per Hyena layer (4x per batch): their per-token work counts once per layer
-PER_LAYER = {"in_proj", "out_proj", "mlp", "toeplitz_conv", "hyena_conv"}
+PER_LAYER = {"in_proj", "out_proj", "mlp", "block", "toeplitz_conv", "hyena_conv"}
 N_LAYERS = 4
 # one Hyena layer as built: dense FLOPs and HBM bytes per token
 LAYER_FLOPS = 2 * 256 * 768 + 2 * 256 * 256 + 2 * 2 * 256 * 1024
-LAYER_BYTES = (512 + 1024) + 1536 + (512 + 1024 + 1024 + 512) + (512 + 1024 + 1024 + 512)
+LAYER_BYTES = (512 + 1024) + 1536 + (512 + 1024 + 1024 + 512)  # front end, long conv, block tail
 
 
 def load_peaks():

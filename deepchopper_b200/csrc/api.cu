@@ -196,7 +196,7 @@ int dcb200_ctx_profile_read(dcb200_ctx* ctx, double* ms, int64_t* counts, int32_
 
 const char* dcb200_kernel_kind_name(int32_t kind) {
   static const char* names[K_NKINDS] = {"encode", "embed_ln", "in_proj", "hyena_conv", "out_proj", "fc1", "fc2",
-                                        "head1", "head2", "smooth_chop", "other", "shortconv_gate", "toeplitz_conv", "mlp"};
+                                        "head1", "head2", "smooth_chop", "other", "shortconv_gate", "toeplitz_conv", "mlp", "block"};
   return (kind >= 0 && kind < K_NKINDS) ? names[kind] : nullptr;
 }
 

@@ -67,7 +67,7 @@ struct DevBuf {
 }  // namespace dcb
 
 namespace dcb {
-enum KernelKind { K_ENCODE = 0, K_EMBED, K_INPROJ, K_CONV, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_SMOOTH, K_OTHER, K_SCONV, K_TOEP, K_MLP, K_NKINDS };
+enum KernelKind { K_ENCODE = 0, K_EMBED, K_INPROJ, K_CONV, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_SMOOTH, K_OTHER, K_SCONV, K_TOEP, K_MLP, K_BLOCK, K_NKINDS };
 struct ProfRec {
   int kind;
   cudaEvent_t a, b;

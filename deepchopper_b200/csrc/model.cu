@@ -4,6 +4,7 @@
 // Reference entry: deepchopper/models/basic_module.py:90-100 -> deepchopper/models/llm/hyena.py:29-41.
 #include "common.cuh"
 #include "fftconv.h"
+#include "block.h"
 #include "gemm.h"
 #include "inproj.h"
 #include "mlp.h"
@@ -34,8 +35,8 @@ struct LayerW {
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
   __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
   CUtensorMap tm_in, tm_out;
-  std::vector<float> hb_fc1, hb_fc2, h_ln1_g, h_ln1_b;  // host copies: passed to kernels as constant-bank parameters
-  CUtensorMap tm_w1u, tm_w2u;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
+  std::vector<float> hb_fc1, hb_fc2, h_ln1_g, h_ln1_b, hb_out, h_ln2_g, h_ln2_b;  // host copies: passed to kernels as constant-bank parameters
+  CUtensorMap tm_w1u, tm_w2u, tm_wou;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
 };
 
 }  // namespace dcb
@@ -254,6 +255,9 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(host_copy(sd, p + "mlp.fc2.bias", kD, lw.hb_fc2));
     DCB_CHECK(host_copy(sd, p + "norm1.weight", kD, lw.h_ln1_g));
     DCB_CHECK(host_copy(sd, p + "norm1.bias", kD, lw.h_ln1_b));
+    DCB_CHECK(host_copy(sd, p + "mixer.out_linear.bias", kD, lw.hb_out));
+    DCB_CHECK(host_copy(sd, p + "norm2.weight", kD, lw.h_ln2_g));
+    DCB_CHECK(host_copy(sd, p + "norm2.bias", kD, lw.h_ln2_b));
     // implicit filter, evaluated once for the whole positional table
     FilterW fw;
     float *z, *t, *w0, *b0, *f1, *w2, *b2, *f3, *w4, *b4, *f5, *w6, *dl;
@@ -283,6 +287,7 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
+    DCB_CHECK(make_tmap_2d(&lw.tm_wou, lw.w_out, kD, kD, 128));
   }
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.weight", kD, &w->lnf_g));
   DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.bias", kD, &w->lnf_b));
@@ -478,6 +483,28 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     }
     DCB_STAGE_DONE();
 
+    const char* blk = getenv("DCB200_BLOCK");
+    if (!(blk && !strcmp(blk, "split"))) {
+      // out_proj + LN2 + MLP + residual + next LN in one kernel: h1 and m never leave the SM
+      static thread_local BlockParams bp;  // 11 KB: keep it off the stack
+      bp.num_pairs = (int)((T / 128 + 1) / 2);
+      bp.T = (int)T;
+      bp.L = L;
+      bp.trace = nullptr;
+      memcpy(bp.bo, lw.hb_out.data(), sizeof(bp.bo));
+      memcpy(bp.ln2_g, lw.h_ln2_g.data(), sizeof(bp.ln2_g));
+      memcpy(bp.ln2_b, lw.h_ln2_b.data(), sizeof(bp.ln2_b));
+      memcpy(bp.b1, lw.hb_fc1.data(), sizeof(bp.b1));
+      memcpy(bp.b2, lw.hb_fc2.data(), sizeof(bp.b2));
+      memcpy(bp.ln_g, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_g.data() : w->h_lnf_g.data(), sizeof(bp.ln_g));
+      memcpy(bp.ln_b, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_b.data() : w->h_lnf_b.data(), sizeof(bp.ln_b));
+      // residual stream updated in place: h (hA) -> h (hA); every tile reads its rows before it writes them
+      DCB_CHECK(launch_block(ctx, tm_y, lw.tm_wou, lw.tm_w1u, lw.tm_w2u, tm_hA, tm_hA, tm_u, bp));
+      DCB_STAGE_DONE();
+      DCB_STAGE_DONE();
+      DCB_STAGE_DONE();
+      continue;
+    }
     p = gp;
     p.bias = lw.b_out;
     p.resid = hA;

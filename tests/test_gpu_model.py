@@ -125,20 +125,16 @@ def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
         y_ref = H.fftconv_ref(v * x1, k, lay.mixer.filter_fn.bias) * x0
         # bf16 activations in and out (and bf16 filter taps on the Toeplitz path): ~0.4 % of the local signal scale
         close("hyena_conv", y, y_ref, 3e-2 * y_ref.pow(2).mean().sqrt().item() + 1e-3, 2e-2)
-        # stage 3: out_proj + residual + LN2
-        run_debug(gpu, tok, qd, 3)
-        hB = read_ws(gpu, "act_hB", (B, L, 256), "f32")
-        m = read_ws(gpu, "act_u", (B, L, 256), "bf16")
-        h1_ref = F.linear(y.transpose(1, 2), bf(lay.mixer.out_linear.weight), lay.mixer.out_linear.bias) + hA
-        close("out_proj+res", hB, h1_ref, 1e-3 + 2e-3 * h1_ref.abs().mean().item(), 1e-3)
-        close("ln2", m, lay.norm2(hB), 1e-2, 1e-2)
-        # stages 4-5: fused MLP (fc1 + gelu + fc2 + residual + next LN1); the hidden activation stays on chip (bf16)
+        # stages 3-5: block tail in one kernel (out_proj + residual + LN2 + fc1 + gelu + fc2 + residual + next LN1);
+        # h1, m and the hidden activation stay on chip, so the reference chain is applied to the GPU's own y
         run_debug(gpu, tok, qd, 5)
         hA2 = read_ws(gpu, "act_hA", (B, L, 256), "f32")
         u2 = read_ws(gpu, "act_u", (B, L, 256), "bf16")
-        g_ref = bf(F.gelu(F.linear(m, bf(lay.mlp.fc1.weight), lay.mlp.fc1.bias), approximate="tanh"))
-        h2_ref = F.linear(g_ref, bf(lay.mlp.fc2.weight), lay.mlp.fc2.bias) + hB
-        close("mlp+res", hA2, h2_ref, 2e-3 + 3e-3 * h2_ref.abs().mean().item(), 1e-3)
+        h1_ref = F.linear(y.transpose(1, 2), bf(lay.mixer.out_linear.weight), lay.mixer.out_linear.bias) + hA
+        m_ref = bf(lay.norm2(h1_ref))
+        g_ref = bf(F.gelu(F.linear(m_ref, bf(lay.mlp.fc1.weight), lay.mlp.fc1.bias), approximate="tanh"))
+        h2_ref = F.linear(g_ref, bf(lay.mlp.fc2.weight), lay.mlp.fc2.bias) + h1_ref
+        close("block tail", hA2, h2_ref, 3e-3 + 4e-3 * h2_ref.abs().mean().item(), 1e-3)
         close("ln1_next", u2, bb.layers[1].norm1(hA2), 1e-2, 1e-2)
 
 
