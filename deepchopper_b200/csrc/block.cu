@@ -28,8 +28,8 @@ constexpr int kThreads = 640;  // 4 service warps + 16 epilogue warps
 constexpr int kSlots = 6;
 constexpr uint32_t kUnitBytes = 128 * 128;  // 128 rows x 64 bf16 (or 2 x 64 rows x 64 bf16)
 constexpr uint32_t kABytes = 4 * kUnitBytes;
-constexpr uint32_t kGBytes = 2 * kUnitBytes;  // one gelu chunk: 128 rows x 128 k
-constexpr int kChunks = 8;                  // 1024 hidden / 128
+constexpr uint32_t kGBytes = 4 * kUnitBytes;  // one gelu chunk: 128 rows x 256 k (four 64-wide K boxes)
+constexpr int kChunks = 4;                  // 1024 hidden / 256: one chunk = one fc1 group
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -52,6 +52,7 @@ __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync
 
 }  // namespace
 
+template <bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWo,
            const __grid_constant__ CUtensorMap tmW1,
@@ -64,9 +65,8 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   if (smem_u32(smem) & 1023u) __trap();
   const uint32_t a_base = smem_u32(smem);
   const uint32_t w_base = a_base + kABytes;
-  const uint32_t g_base = w_base + kSlots * kUnitBytes;  // G (also staging slots s0, s1 at the end of a tile)
-  const uint32_t r_base = g_base + kGBytes;              // dedicated staging slots D0, D1
-  uint8_t* tail = smem + kABytes + kSlots * kUnitBytes + kGBytes + 2 * kUnitBytes;
+  const uint32_t g_base = w_base + kSlots * kUnitBytes;  // G: K box `part` doubles as part's staging slot between tiles
+  uint8_t* tail = smem + kABytes + kSlots * kUnitBytes + kGBytes;
   float2* stats = reinterpret_cast<float2*>(tail);  // [2 part pairs][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * 128 * 8);
   const uint32_t bar_base = smem_u32(bars);
@@ -124,12 +124,17 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   const bool traced = p.trace != nullptr && blockIdx.x == 0;
   const int pair0 = (int)cluster_id_x(), pair_step = (int)cluster_nclusters_x();
 
+  // Register budget: the four service warps (one lane each of scalar code) give registers up so that the 512 epilogue
+  // threads can hold a 64-column accumulator slice plus the LayerNorm state without spilling (with 227 KB of shared
+  // memory there is no L1 to absorb local-memory traffic).  128 x 64 + 512 x 104 <= 640 x 96.
+  if (warp < 4) {
+  setmaxnreg_dec<64>();
   if (warp == 0) {
     // ===== weight-ring producer (both CTAs) =====
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      Tracer tr{traced ? p.trace + 2 * 2 * kTraceCap : nullptr, 0};
+      TracerT<kTrace> tr{traced ? p.trace + 2 * 2 * kTraceCap : nullptr, 0};
       uint32_t wfull[kSlots];
       for (int s = 0; s < kSlots; ++s) wfull[s] = lbar(W_FULL + s);
       auto advance = [&]() {
@@ -149,14 +154,14 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           advance();
         }
       };
-      // fc2 chunk j: my 128 rows (output features) of W2 x K = 128 -> two slots of 64 k
+      // fc2 chunk j: my 128 rows (output features) of W2 x K = 256 -> four slots of 64 k
       auto load_fc2 = [&](int j) {
-        for (int kb = 0; kb < 2; ++kb) {
+        for (int kb = 0; kb < 4; ++kb) {
           tr(320 + j);
           mbar_wait(bar(W_EMPTY + slot), phase ^ 1);
           tr(330 + j);
           if (leader) mbar_arrive_expect_tx(bar(W_FULL + slot), 2 * kUnitBytes);
-          tma_load_2d_2sm(w_base + slot * kUnitBytes, &tmW2, wfull[slot], j * 128 + kb * 64, (int)rank * 128);
+          tma_load_2d_2sm(w_base + slot * kUnitBytes, &tmW2, wfull[slot], j * 256 + kb * 64, (int)rank * 128);
           advance();
         }
       };
@@ -170,12 +175,11 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         }
       };
       for (int pr = pair0; pr < num_pairs; pr += pair_step) {
-        load_wo();
+        load_wo();  // (the order of the MMA warp)
         load_fc1(0);
-        for (int P = 0; P < kChunks / 2; ++P) {
-          load_fc2(2 * P);
-          if (P + 1 < kChunks / 2) load_fc1(P + 1);
-          load_fc2(2 * P + 1);
+        for (int P = 0; P < kChunks; ++P) {
+          if (P + 1 < kChunks) load_fc1(P + 1);
+          load_fc2(P);
         }
       }
     }
@@ -188,7 +192,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       uint32_t n = 0;   // tile pairs done by this cluster
       uint32_t t1 = 0;  // uses of acc1 started so far (out_proj + 4 fc1 groups per tile)
       constexpr uint32_t idesc_o = make_idesc_bf16(256, 256, true, false);  // A = y tile, MN-major
-      Tracer tr{traced ? p.trace : nullptr, 0};
+      TracerT<kTrace> tr{traced ? p.trace : nullptr, 0};
       auto advance = [&]() {
         if (++slot == kSlots) {
           slot = 0;
@@ -217,16 +221,16 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             advance();
           }
           umma_commit_2sm(bar(T1_FULL), 3);
-          if (P == kChunks / 2 - 1) umma_commit_2sm(bar(A_EMPTY), 3);
+          if (P == kChunks - 1) umma_commit_2sm(bar(A_EMPTY), 3);
         };
         auto fc2 = [&](int j) {
           tr(200 + j);
-          mbar_wait_cluster(bar(G_FULL), j & 1);  // (8 uses per tile: parity of 8 n + j)
+          mbar_wait_cluster(bar(G_FULL), j & 1);  // (4 uses per tile: parity of 4 n + j)
           tr(210 + j);
           if (j == 0) mbar_wait_cluster(bar(T2_EMPTY), (n & 1) ^ 1);
           tr(220 + j);
           tc_fence_after();
-          for (int kb = 0; kb < 2; ++kb) {
+          for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(bar(W_FULL + slot), wphase);
             tr(230 + j);
             tc_fence_after();
@@ -263,11 +267,12 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         mbar_wait_cluster(bar(M_FULL), n & 1);  // m tile written over the y tile, acc2 preloaded (both CTAs)
         tr(93);
         tc_fence_after();
+        // fc1(P + 1) goes ahead of fc2(P): acc1 is free as soon as the epilogue holds group P in registers, G(P) only
+        // after its GELU, so the tensor pipe works on fc1(P + 1) while the epilogue warps compute GELU(P).
         fc1(0);
-        for (int P = 0; P < kChunks / 2; ++P) {
-          fc2(2 * P);
-          if (P + 1 < kChunks / 2) fc1(P + 1);  // acc1 is free once the epilogue holds its second half in registers
-          fc2(2 * P + 1);
+        for (int P = 0; P < kChunks; ++P) {
+          if (P + 1 < kChunks) fc1(P + 1);
+          fc2(P);
         }
       }
     }
@@ -292,7 +297,9 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         load_y(pr + pair_step);
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    setmaxnreg_inc<104>();
     // ===== epilogue: 16 warps = 4 TMEM lane quadrants x 4 column parts =====
     const int quad = warp & 3;
     const int part = (warp - 4) >> 2;  // 0..3
@@ -305,13 +312,13 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     const uint32_t t2_empty = lbar(T2_EMPTY);
     uint32_t n = 0;
     uint32_t v[32];
-    Tracer tr{(traced && warp == 4 && lane == 0) ? p.trace + 2 * kTraceCap : nullptr, 0};
+    TracerT<kTrace> tr{(traced && warp == 4 && lane == 0) ? p.trace + 2 * kTraceCap : nullptr, 0};
     const uint64_t kC0 = f2_pack(0.7978845608f, 0.7978845608f), kC1 = f2_pack(0.0356774081f, 0.0356774081f);
     const uint64_t kHalf = f2_pack(0.5f, 0.5f);
-    // Final-epilogue staging: part p owns the columns [64p, 64p+64) and ONE 16 KB slot (parts 0,1 the dedicated D0,D1,
-    // parts 2,3 the halves of G, dead once the tile's last fc2 has retired) through which its two fp32 h_out boxes and
-    // its bf16 u box go to TMA stores.
-    const uint32_t my_slot = part < 2 ? r_base + part * kUnitBytes : g_base + (part - 2) * kUnitBytes;
+    // Final-epilogue staging: part p owns the columns [64p, 64p+64) and ONE 16 KB slot (K box p of G, dead once the
+    // tile's last fc2 has retired and until GELU(0) of the next tile) through which its two fp32 h_out boxes and its
+    // bf16 u box go to TMA stores.
+    const uint32_t my_slot = g_base + part * kUnitBytes;
     // Epilogue O stages the residual through the same slot: box 2 part (columns [64 part, +32)) is loaded one tile
     // ahead, box 2 part + 1 as soon as the first has been consumed.
     const uint32_t my_rfull = bar(R_FULL + part);
@@ -410,52 +417,59 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         if (lane == 0) mbar_arrive_remote(m_full);
         bar_sync(6 + quad, 128);  // (stats are rewritten by the final epilogue of this tile)
       }
-      // ---- GELU chunks: acc1[s] -> bf16 K-major tile G[s]; my 32 of the chunk's 128 columns ---------------------
+      // ---- GELU chunks: acc1 (one fc1 group, 256 hidden units) -> bf16 K-major tile G; my 64 of the 256 columns = my
+      // row of K box `part`.  acc1 goes back to the MMA warp as soon as the group sits in registers.
+#pragma unroll 1
       for (int j = 0; j < kChunks; ++j) {
-        const int s = j & 1;  // which 128-column half of acc1
+        uint32_t w2[32];
         tr(400 + j);
-        if (s == 0) {  // fc1 group j/2
-          mbar_wait(bar(T1_FULL), e1 & 1);
-          ++e1;
-        }
+        mbar_wait(bar(T1_FULL), e1 & 1);
+        ++e1;
         tr(410 + j);
         tc_fence_after();
-        tmem_ld32(tmem_base + lane_off + 256 + 128 * s + part * 32, v);
-        const float* b1 = p.b1 + j * 128 + part * 32;  // kernel-parameter (constant bank) array, warp-uniform index
+        tmem_ld32(tmem_base + lane_off + 256 + colA, v);
+        tmem_ld32(tmem_base + lane_off + 256 + colA + 32, w2);
         tmem_ld_wait();
-        // acc1 is free as soon as its second half sits in registers: fc1 of the next group may start
         tc_fence_before();
         __syncwarp();
-        if (s == 1 && lane == 0) mbar_arrive_remote(t1_empty);
-        const uint32_t grow = g_base + (part >> 1) * kUnitBytes + row * 128;
-        uint32_t o[16];
+        if (lane == 0) mbar_arrive_remote(t1_empty);
+        const float* b1 = p.b1 + j * 256 + colA;  // kernel-parameter (constant bank) array, warp-uniform index
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float bj[8];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t (&x)[32] = c ? w2 : v;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bj[i] = b1[q * 8 + i];
+          for (int q = 0; q < 4; ++q) {
+            float bj[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // gelu_tanh on a pair: 0.5 x (1 + tanh(x (c0 + c1 x^2))), packed fp32x2 arithmetic
-            const uint64_t x = f2_add(f2_pack(__uint_as_float(v[q * 8 + 2 * i]), __uint_as_float(v[q * 8 + 2 * i + 1])),
-                                      f2_pack(bj[2 * i], bj[2 * i + 1]));
-            const uint64_t in = f2_fma(f2_mul(x, x), kC1, kC0);
-            float u0, u1, t0, t1;
-            f2_unpack(f2_mul(x, in), u0, u1);
-            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
-            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
-            const uint64_t hx = f2_mul(x, kHalf);
-            float y0, y1;
-            f2_unpack(f2_fma(hx, f2_pack(t0, t1), hx), y0, y1);
-            o[q * 4 + i] = pack_bf16(y0, y1);
+            for (int i = 0; i < 8; ++i) bj[i] = b1[c * 32 + q * 8 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              // gelu_tanh on a pair: 0.5 x (1 + tanh(x (c0 + c1 x^2))), packed fp32x2 arithmetic
+              const uint64_t xx = f2_add(f2_pack(__uint_as_float(x[q * 8 + 2 * i]), __uint_as_float(x[q * 8 + 2 * i + 1])),
+                                         f2_pack(bj[2 * i], bj[2 * i + 1]));
+              const uint64_t in = f2_fma(f2_mul(xx, xx), kC1, kC0);
+              float u0, u1, t0, t1;
+              f2_unpack(f2_mul(xx, in), u0, u1);
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+              const uint64_t hx = f2_mul(xx, kHalf);
+              float y0, y1;
+              f2_unpack(f2_fma(hx, f2_pack(t0, t1), hx), y0, y1);
+              x[q * 4 + i] = pack_bf16(y0, y1);  // (in place: index q*4+i <= q*8+2i)
+            }
           }
         }
         tr(420 + j);
-        mbar_wait(bar(G_EMPTY), (j & 1) ^ 1);  // fc2 of the previous chunk has finished reading G (parity of 8 n + j - 1)
+        mbar_wait(bar(G_EMPTY), (j & 1) ^ 1);  // fc2 of the previous chunk has finished reading G (parity of 4 n + j - 1)
         tr(430 + j);
+        const uint32_t grow = my_slot + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          sts128(grow + (((uint32_t)((part & 1) * 4 + q) ^ sw) << 4), o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t (&x)[32] = c ? w2 : v;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(grow + (((uint32_t)(c * 4 + q) ^ sw) << 4), x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(g_full);
@@ -574,8 +588,9 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 int launch_block(dcb200_ctx* ctx, const CUtensorMap& tm_y, const CUtensorMap& tm_wo, const CUtensorMap& tm_w1,
                  const CUtensorMap& tm_w2, const CUtensorMap& tm_hin, const CUtensorMap& tm_hout, const CUtensorMap& tm_u,
                  const BlockParams& p) {
-  const size_t smem = kABytes + kSlots * kUnitBytes + kGBytes + 2 * kUnitBytes + 2 * 128 * 8 + 48 * 8;
-  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&block_kernel), smem));
+  const size_t smem = kABytes + kSlots * kUnitBytes + kGBytes + 2 * 128 * 8 + 48 * 8;
+  auto kern = p.trace ? &block_kernel<true> : &block_kernel<false>;
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(kern), smem));
   int clusters = ctx->sm_count / 2;
   if (p.num_pairs < clusters) clusters = p.num_pairs;
   cudaLaunchConfig_t cfg;
@@ -592,7 +607,7 @@ int launch_block(dcb200_ctx* ctx, const CUtensorMap& tm_y, const CUtensorMap& tm
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(ctx, K_BLOCK);
-  DCB_CUDA(cudaLaunchKernelEx(&cfg, block_kernel, tm_y, tm_wo, tm_w1, tm_w2, tm_hin, tm_hout, tm_u, p));
+  DCB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_y, tm_wo, tm_w1, tm_w2, tm_hin, tm_hout, tm_u, p));
   ctx->launches++;
   return DCB200_OK;
 }

@@ -491,6 +491,12 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       bp.T = (int)T;
       bp.L = L;
       bp.trace = nullptr;
+      if (l == 0 && getenv("DCB200_TRACE") && !strcmp(getenv("DCB200_TRACE"), "block")) {
+        DevBuf& bt = ctx->buf("trace");
+        DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
+        DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
+        bp.trace = bt.as<long long>();
+      }
       memcpy(bp.bo, lw.hb_out.data(), sizeof(bp.bo));
       memcpy(bp.ln2_g, lw.h_ln2_g.data(), sizeof(bp.ln2_g));
       memcpy(bp.ln2_b, lw.h_ln2_b.data(), sizeof(bp.ln2_b));

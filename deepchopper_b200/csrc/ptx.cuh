@@ -147,6 +147,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// Register reallocation between warpgroups (4 consecutive warps execute it together).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -357,6 +362,21 @@ struct Tracer {
       buf[2 * n] = tag;
       buf[2 * n + 1] = clock64();
       ++n;
+    }
+  }
+};
+// Compile-time switch: kernels instantiated with On = false carry no trace code at all.
+template <bool On>
+struct TracerT {
+  long long* buf;
+  int n;
+  __device__ __forceinline__ void operator()(int tag) {
+    if constexpr (On) {
+      if (buf && n < kTraceCap) {
+        buf[2 * n] = tag;
+        buf[2 * n + 1] = clock64();
+        ++n;
+      }
     }
   }
 };

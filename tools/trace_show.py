@@ -4,7 +4,7 @@ tile = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 for sec in txt.split('== ')[1:]:
     name = sec.split('\n')[0]
     ev = [(int(a), int(b)) for a, b in re.findall(r'(\d+)@(-?\d+)', sec)]
-    start = {"MMA": 90, "EPI": 400, "PROD": 300}[name]
+    start = {"MMA": 90, "EPI": 380 if "380@" in txt else 400, "PROD": 300}[name]
     if len(sys.argv) > 3 and sys.argv[3] == "raw":
         print("==", name)
         print(" ".join(f"{t}:{c - ev[0][1]}" for t, c in ev[:int(sys.argv[4]) if len(sys.argv) > 4 else 120]))
