@@ -25,7 +25,10 @@ using namespace ptx;
 namespace {
 
 constexpr int kThreads = 640;  // 4 service warps + 16 epilogue warps
-constexpr int kSlots = 6;
+constexpr int kSlots = 5;  // weight ring (80 KB); the sixth slot's room holds the bias / LayerNorm vectors
+// fp32 vectors in shared memory, read with warp-uniform (broadcast) LDS.128: an indexed constant-bank load (LDC.64)
+// issues at a few cycles per warp, and at 640 values per thread per tile that was ~14 % of the kernel.
+enum { V_BO = 0, V_LN2G = 256, V_LN2B = 512, V_B2 = 768, V_LNG = 1024, V_LNB = 1280, V_B1 = 1536, V_FLOATS = 2560 };
 constexpr uint32_t kUnitBytes = 128 * 128;  // 128 rows x 64 bf16 (or 2 x 64 rows x 64 bf16)
 constexpr uint32_t kABytes = 4 * kUnitBytes;
 constexpr uint32_t kGBytes = 4 * kUnitBytes;  // one gelu chunk: 128 rows x 256 k (four 64-wide K boxes)
@@ -66,7 +69,9 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   const uint32_t a_base = smem_u32(smem);
   const uint32_t w_base = a_base + kABytes;
   const uint32_t g_base = w_base + kSlots * kUnitBytes;  // G: K box `part` doubles as part's staging slot between tiles
-  uint8_t* tail = smem + kABytes + kSlots * kUnitBytes + kGBytes;
+  const uint32_t vec_base = g_base + kGBytes;
+  float* vecs = reinterpret_cast<float*>(smem + kABytes + kSlots * kUnitBytes + kGBytes);
+  uint8_t* tail = smem + kABytes + kSlots * kUnitBytes + kGBytes + V_FLOATS * 4;
   float2* stats = reinterpret_cast<float2*>(tail);  // [2 part pairs][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * 128 * 8);
   const uint32_t bar_base = smem_u32(bars);
@@ -75,7 +80,8 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   enum { A_FULL = 0 /*L*/, A_EMPTY = 1 /*B*/, W_FULL = 2 /*L*/, W_EMPTY = W_FULL + kSlots /*B*/,
          T1_FULL = W_EMPTY + kSlots /*B*/, T1_EMPTY = T1_FULL + 1 /*L*/, G_FULL = T1_EMPTY + 1 /*L*/,
          G_EMPTY = G_FULL + 1 /*B*/, T2_FULL = G_EMPTY + 1 /*B*/, T2_EMPTY = T2_FULL + 1 /*L*/,
-         R_FULL = T2_EMPTY + 1 /*local: one per staging slot*/, M_FULL = R_FULL + 4 /*L*/, N_BARS = M_FULL + 1 };
+         R_FULL = T2_EMPTY + 1 /*local: one per staging slot*/, R2_FULL = R_FULL + 4 /*local: one per K box of A*/,
+         M_FULL = R2_FULL + 4 /*L*/, Y_DEAD = M_FULL + 1 /*B*/, N_BARS = Y_DEAD + 1 };
   auto bar = [&](int i) { return bar_base + 8u * i; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
@@ -107,10 +113,23 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     mbar_init(bar(G_EMPTY), 1);
     mbar_init(bar(T2_FULL), 1);
     mbar_init(bar(T2_EMPTY), 32);
-    for (int s = 0; s < 4; ++s) mbar_init(bar(R_FULL + s), 1);
+    for (int s = 0; s < 8; ++s) mbar_init(bar(R_FULL + s), 1);
     mbar_init(bar(M_FULL), 32);
+    mbar_init(bar(Y_DEAD), 1);
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    vecs[V_BO + i] = p.bo[i];
+    vecs[V_LN2G + i] = p.ln2_g[i];
+    vecs[V_LN2B + i] = p.ln2_b[i];
+    vecs[V_B2 + i] = p.b2[i];
+    vecs[V_LNG + i] = p.ln_g[i];
+    vecs[V_LNB + i] = p.ln_b[i];
+  }
+  for (int i = threadIdx.x; i < 1024; i += kThreads) vecs[V_B1 + i] = p.b1[i];
+  auto vec4 = [&](int idx, float (&o)[4]) {  // four consecutive vector elements, same address in every lane
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(vec_base + 4u * idx));
+  };
   if (warp == 2) {
     tmem_alloc_2sm(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish_2sm();
@@ -263,6 +282,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           advance();
         }
         umma_commit_2sm(bar(T1_FULL), 3);
+        umma_commit_2sm(bar(Y_DEAD), 3);
         tr(92);
         mbar_wait_cluster(bar(M_FULL), n & 1);  // m tile written over the y tile, acc2 preloaded (both CTAs)
         tr(93);
@@ -273,6 +293,21 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         for (int P = 0; P < kChunks; ++P) {
           if (P + 1 < kChunks) fc1(P + 1);
           fc2(P);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== second residual boxes: columns [64 part + 32, +32) of h0 land in K box `part` of the A buffer as soon as the
+    // out_proj MMAs have retired (the y tile is dead from then until m is written over it), i.e. while the epilogue
+    // warps are still busy with the previous tile's stores: epilogue O finds them resident.
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int pr = pair0; pr < num_pairs; pr += pair_step, ++n) {
+        const int tok0 = pr * 256 + (int)rank * 128;
+        mbar_wait(bar(Y_DEAD), n & 1);
+        for (int q = 0; q < 4; ++q) {
+          mbar_arrive_expect_tx(bar(R2_FULL + q), kUnitBytes);
+          tma_load_2d(a_base + q * kUnitBytes, &tmHin, bar(R2_FULL + q), q * 64 + 32, tok0);
         }
       }
     }
@@ -319,11 +354,10 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     // tile's last fc2 has retired and until GELU(0) of the next tile) through which its two fp32 h_out boxes and its
     // bf16 u box go to TMA stores.
     const uint32_t my_slot = g_base + part * kUnitBytes;
-    // Epilogue O stages the residual through the same slot: box 2 part (columns [64 part, +32)) is loaded one tile
-    // ahead, box 2 part + 1 as soon as the first has been consumed.
+    // Epilogue O takes the first residual box (columns [64 part, +32)) through the same slot (requested at the end of
+    // the previous tile) and the second from the A buffer (warp 2).
     const uint32_t my_rfull = bar(R_FULL + part);
     const uint32_t m_full = lbar(M_FULL);
-    uint32_t rphase = 0;
     uint32_t e1 = 0;  // uses of acc1 consumed so far
     const int colA = part * 64;
     if (storer && pair0 < num_pairs) {
@@ -335,8 +369,10 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       // ---- epilogue O: x1 = acc1 + bo + h0 ; m = LN2(x1) -> A tile of fc1 ; acc2 := x1 + b2 ---------------------------
       {
         uint32_t w2[32];
+        tr(380);
         mbar_wait(bar(T1_FULL), e1 & 1);
         ++e1;
+        tr(381);
         tc_fence_after();
         tmem_ld32(tmem_base + lane_off + 256 + colA, v);
         tmem_ld32(tmem_base + lane_off + 256 + colA + 32, w2);
@@ -344,33 +380,33 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(t1_empty);  // acc1 drained
+        tr(382);
         float sum = 0.f, sq = 0.f;
-        const uint32_t rrow = my_slot + row * 128;
+        // The box in the A buffer (my columns 32-63) has been resident for a while; the one in my staging slot (columns
+        // 0-31) was requested at the very end of the previous tile, so it goes second.
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
-          uint32_t (&x)[32] = st ? w2 : v;
-          mbar_wait(my_rfull, rphase);
-          rphase ^= 1;
+          uint32_t (&x)[32] = st ? v : w2;
+          const uint32_t rrow = (st ? my_slot : a_base + part * kUnitBytes) + row * 128;
+          const int c0 = colA + (st ? 0 : 32);
+          mbar_wait(st ? my_rfull : bar(R2_FULL + part), n & 1);
+          tr(383 + st);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             uint32_t r[4];
+            float c4[4];
             lds128(rrow + (((uint32_t)q ^ sw) << 4), r);
+            vec4(V_BO + c0 + 4 * q, c4);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float xv = __uint_as_float(x[4 * q + i]) + p.bo[colA + st * 32 + 4 * q + i] + __uint_as_float(r[i]);
+              const float xv = __uint_as_float(x[4 * q + i]) + c4[i] + __uint_as_float(r[i]);
               sum += xv;
               sq = fmaf(xv, xv, sq);
               x[4 * q + i] = __float_as_uint(xv);
             }
           }
-          if (st == 0) {
-            bar_sync(2 + part, 128);  // all four warps of the part have consumed the box
-            if (storer) {
-              mbar_arrive_expect_tx(my_rfull, kUnitBytes);
-              tma_load_2d(my_slot, &tmHin, my_rfull, colA + 32, tok0);
-            }
-          }
         }
+        tr(385);
         float2* st2 = stats + (part >> 1) * 128 + row;
         if (part & 1) *st2 = make_float2(sum, sq);
         bar_sync(6 + quad, 128);
@@ -379,6 +415,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           *st2 = make_float2(sum + o.x, sq + o.y);
         }
         bar_sync(6 + quad, 128);
+        tr(386);
         float2 sa = stats[row];
         {
           const float2 sb = stats[128 + row];
@@ -395,19 +432,30 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = colA + c * 32 + q * 8;
-            float y[8];
+            float y[8], g8[8], b8[8];
+            vec4(V_LN2G + col, *reinterpret_cast<float(*)[4]>(g8));
+            vec4(V_LN2G + col + 4, *reinterpret_cast<float(*)[4]>(g8 + 4));
+            vec4(V_LN2B + col, *reinterpret_cast<float(*)[4]>(b8));
+            vec4(V_LN2B + col + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, p.ln2_g[col + i], p.ln2_b[col + i]);
+            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, g8[i], b8[i]);
             sts128(mrow + (((uint32_t)(c * 4 + q) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
                    pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
           }
         }
         // acc2 := x1 + b2: fc2 accumulates onto the residual
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = __float_as_uint(__uint_as_float(v[i]) + p.b2[colA + i]);
-          w2[i] = __float_as_uint(__uint_as_float(w2[i]) + p.b2[colA + 32 + i]);
+        for (int q = 0; q < 8; ++q) {
+          float c4[4], d4[4];
+          vec4(V_B2 + colA + 4 * q, c4);
+          vec4(V_B2 + colA + 32 + 4 * q, d4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[4 * q + i] = __float_as_uint(__uint_as_float(v[4 * q + i]) + c4[i]);
+            w2[4 * q + i] = __float_as_uint(__uint_as_float(w2[4 * q + i]) + d4[i]);
+          }
         }
+        tr(387);
         tmem_st32(tmem_base + lane_off + colA, v);
         tmem_st32(tmem_base + lane_off + colA + 32, w2);
         tmem_st_wait();
@@ -415,6 +463,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(m_full);
+        tr(388);
         bar_sync(6 + quad, 128);  // (stats are rewritten by the final epilogue of this tile)
       }
       // ---- GELU chunks: acc1 (one fc1 group, 256 hidden units) -> bf16 K-major tile G; my 64 of the 256 columns = my
@@ -433,15 +482,15 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(t1_empty);
-        const float* b1 = p.b1 + j * 256 + colA;  // kernel-parameter (constant bank) array, warp-uniform index
+        const int b1o = V_B1 + j * 256 + colA;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t (&x)[32] = c ? w2 : v;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float bj[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bj[i] = b1[c * 32 + q * 8 + i];
+            vec4(b1o + c * 32 + q * 8, *reinterpret_cast<float(*)[4]>(bj));
+            vec4(b1o + c * 32 + q * 8 + 4, *reinterpret_cast<float(*)[4]>(bj + 4));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               // gelu_tanh on a pair: 0.5 x (1 + tanh(x (c0 + c1 x^2))), packed fp32x2 arithmetic
@@ -543,9 +592,13 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = colA + c * 32 + q * 8;
-            float y[8];
+            float y[8], g8[8], b8[8];
+            vec4(V_LNG + col, *reinterpret_cast<float(*)[4]>(g8));
+            vec4(V_LNG + col + 4, *reinterpret_cast<float(*)[4]>(g8 + 4));
+            vec4(V_LNB + col, *reinterpret_cast<float(*)[4]>(b8));
+            vec4(V_LNB + col + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, p.ln_g[col + i], p.ln_b[col + i]);
+            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, g8[i], b8[i]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[q * 4 + i] = pack_bf16(y[2 * i], y[2 * i + 1]);  // (in place: index q*4+i <= q*8+2i)
           }
@@ -588,7 +641,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 int launch_block(dcb200_ctx* ctx, const CUtensorMap& tm_y, const CUtensorMap& tm_wo, const CUtensorMap& tm_w1,
                  const CUtensorMap& tm_w2, const CUtensorMap& tm_hin, const CUtensorMap& tm_hout, const CUtensorMap& tm_u,
                  const BlockParams& p) {
-  const size_t smem = kABytes + kSlots * kUnitBytes + kGBytes + 2 * 128 * 8 + 48 * 8;
+  const size_t smem = kABytes + kSlots * kUnitBytes + kGBytes + V_FLOATS * 4 + 2 * 128 * 8 + 56 * 8;
   auto kern = p.trace ? &block_kernel<true> : &block_kernel<false>;
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(kern), smem));
   int clusters = ctx->sm_count / 2;
