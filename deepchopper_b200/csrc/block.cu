@@ -381,7 +381,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(t1_empty);  // acc1 drained
         tr(382);
-        float sum = 0.f, sq = 0.f;
+        uint64_t sum2 = f2_pack(0.f, 0.f), sq2 = sum2;  // (even, odd) column partial sums: packed fp32x2 arithmetic
         // The box in the A buffer (my columns 32-63) has been resident for a while; the one in my staging slot (columns
         // 0-31) was requested at the very end of the previous tile, so it goes second.
 #pragma unroll
@@ -398,13 +398,26 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             lds128(rrow + (((uint32_t)q ^ sw) << 4), r);
             vec4(V_BO + c0 + 4 * q, c4);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float xv = __uint_as_float(x[4 * q + i]) + c4[i] + __uint_as_float(r[i]);
-              sum += xv;
-              sq = fmaf(xv, xv, sq);
-              x[4 * q + i] = __float_as_uint(xv);
+            for (int i = 0; i < 4; i += 2) {
+              const uint64_t xv = f2_add(f2_add(f2_pack(__uint_as_float(x[4 * q + i]), __uint_as_float(x[4 * q + i + 1])),
+                                                f2_pack(c4[i], c4[i + 1])),
+                                         f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+              sum2 = f2_add(sum2, xv);
+              sq2 = f2_fma(xv, xv, sq2);
+              float x0, x1;
+              f2_unpack(xv, x0, x1);
+              x[4 * q + i] = __float_as_uint(x0);
+              x[4 * q + i + 1] = __float_as_uint(x1);
             }
           }
+        }
+        float sum, sq;
+        {
+          float a0, a1, b0, b1;
+          f2_unpack(sum2, a0, a1);
+          f2_unpack(sq2, b0, b1);
+          sum = a0 + a1;
+          sq = b0 + b1;
         }
         tr(385);
         float2* st2 = stats + (part >> 1) * 128 + row;
@@ -424,35 +437,36 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         }
         const float mean = sa.x * (1.0f / 256.0f);
         const float rstd = rsqrtf(fmaxf(sa.y * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
-        // m: my 64 columns = K box `part` of the fc1 A tile (over the y tile: every out_proj MMA has retired)
+        // m: my 64 columns = K box `part` of the fc1 A tile (over the y tile: every out_proj MMA has retired);
+        // acc2 := x1 + b2: fc2 accumulates onto the residual.  Packed fp32x2: z = x rstd - mean rstd ; m = z g + b.
         const uint32_t mrow = a_base + part * kUnitBytes + row * 128;
+        const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const uint32_t (&x)[32] = c ? w2 : v;
+          uint32_t (&x)[32] = c ? w2 : v;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = colA + c * 32 + q * 8;
-            float y[8], g8[8], b8[8];
+            float g8[8], b8[8], d8[8];
+            uint32_t o[4];
             vec4(V_LN2G + col, *reinterpret_cast<float(*)[4]>(g8));
             vec4(V_LN2G + col + 4, *reinterpret_cast<float(*)[4]>(g8 + 4));
             vec4(V_LN2B + col, *reinterpret_cast<float(*)[4]>(b8));
             vec4(V_LN2B + col + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
+            vec4(V_B2 + col, *reinterpret_cast<float(*)[4]>(d8));
+            vec4(V_B2 + col + 4, *reinterpret_cast<float(*)[4]>(d8 + 4));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, g8[i], b8[i]);
-            sts128(mrow + (((uint32_t)(c * 4 + q) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
-                   pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-          }
-        }
-        // acc2 := x1 + b2: fc2 accumulates onto the residual
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float c4[4], d4[4];
-          vec4(V_B2 + colA + 4 * q, c4);
-          vec4(V_B2 + colA + 32 + 4 * q, d4);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[4 * q + i] = __float_as_uint(__uint_as_float(v[4 * q + i]) + c4[i]);
-            w2[4 * q + i] = __float_as_uint(__uint_as_float(w2[4 * q + i]) + d4[i]);
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t xv = f2_pack(__uint_as_float(x[q * 8 + 2 * i]), __uint_as_float(x[q * 8 + 2 * i + 1]));
+              const uint64_t z = f2_fma(xv, rs2, nm2);
+              float y0, y1, a0, a1;
+              f2_unpack(f2_fma(z, f2_pack(g8[2 * i], g8[2 * i + 1]), f2_pack(b8[2 * i], b8[2 * i + 1])), y0, y1);
+              o[i] = pack_bf16(y0, y1);
+              f2_unpack(f2_add(xv, f2_pack(d8[2 * i], d8[2 * i + 1])), a0, a1);
+              x[q * 8 + 2 * i] = __float_as_uint(a0);
+              x[q * 8 + 2 * i + 1] = __float_as_uint(a1);
+            }
+            sts128(mrow + (((uint32_t)(c * 4 + q) ^ sw) << 4), o[0], o[1], o[2], o[3]);
           }
         }
         tr(387);
@@ -539,12 +553,21 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(t2_empty);  // acc2 drained
-      float sum = 0.f, sq = 0.f;
+      float sum, sq;
+      {
+        uint64_t sum2 = f2_pack(0.f, 0.f), sq2 = sum2;  // (b2 and the residual are already in acc2)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float xa = __uint_as_float(v[i]), xb = __uint_as_float(v2[i]);  // (b2 and the residual are already in acc2)
-        sum += xa + xb;
-        sq = fmaf(xa, xa, fmaf(xb, xb, sq));
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t xa = f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          const uint64_t xb = f2_pack(__uint_as_float(v2[i]), __uint_as_float(v2[i + 1]));
+          sum2 = f2_add(sum2, f2_add(xa, xb));
+          sq2 = f2_fma(xa, xa, f2_fma(xb, xb, sq2));
+        }
+        float a0, a1, b0, b1;
+        f2_unpack(sum2, a0, a1);
+        f2_unpack(sq2, b0, b1);
+        sum = a0 + a1;
+        sq = b0 + b1;
       }
       // row statistics (sum, sum of squares) over the four column parts, in a fixed order: (p0 + p1) + (p2 + p3)
       float2* st2 = stats + (part >> 1) * 128 + row;
@@ -585,6 +608,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       }
       const float mean = sa.x * (1.0f / 256.0f);
       const float rstd = rsqrtf(fmaxf(sa.y * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
+      const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
       {  // u: my 64 bf16 columns (128 B per row), normalised in registers while the second h_out store drains
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -592,15 +616,18 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = colA + c * 32 + q * 8;
-            float y[8], g8[8], b8[8];
+            float g8[8], b8[8];
             vec4(V_LNG + col, *reinterpret_cast<float(*)[4]>(g8));
             vec4(V_LNG + col + 4, *reinterpret_cast<float(*)[4]>(g8 + 4));
             vec4(V_LNB + col, *reinterpret_cast<float(*)[4]>(b8));
             vec4(V_LNB + col + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaf((__uint_as_float(x[q * 8 + i]) - mean) * rstd, g8[i], b8[i]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[q * 4 + i] = pack_bf16(y[2 * i], y[2 * i + 1]);  // (in place: index q*4+i <= q*8+2i)
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t z = f2_fma(f2_pack(__uint_as_float(x[q * 8 + 2 * i]), __uint_as_float(x[q * 8 + 2 * i + 1])), rs2, nm2);
+              float y0, y1;
+              f2_unpack(f2_fma(z, f2_pack(g8[2 * i], g8[2 * i + 1]), f2_pack(b8[2 * i], b8[2 * i + 1])), y0, y1);
+              x[q * 4 + i] = pack_bf16(y0, y1);  // (in place: index q*4+i <= q*8+2i)
+            }
           }
         }
         bar_sync(2 + part, 128);  // slot free again
