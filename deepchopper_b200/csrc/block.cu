@@ -28,7 +28,7 @@ constexpr int kThreads = 640;  // 4 service warps + 16 epilogue warps
 constexpr int kSlots = 5;  // weight ring (80 KB); the sixth slot's room holds the bias / LayerNorm vectors
 // fp32 vectors in shared memory, read with warp-uniform (broadcast) LDS.128: an indexed constant-bank load (LDC.64)
 // issues at a few cycles per warp, and at 640 values per thread per tile that was ~14 % of the kernel.
-enum { V_BO = 0, V_LN2G = 256, V_LN2B = 512, V_B2 = 768, V_LNG = 1024, V_LNB = 1280, V_B1 = 1536, V_FLOATS = 2560 };
+enum { V_BO = 0, V_B2 = 256, V_B1 = 512, V_FLOATS = 1536 };
 constexpr uint32_t kUnitBytes = 128 * 128;  // 128 rows x 64 bf16 (or 2 x 64 rows x 64 bf16)
 constexpr uint32_t kABytes = 4 * kUnitBytes;
 constexpr uint32_t kGBytes = 4 * kUnitBytes;  // one gelu chunk: 128 rows x 256 k (four 64-wide K boxes)
@@ -120,11 +120,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   }
   for (int i = threadIdx.x; i < 256; i += kThreads) {
     vecs[V_BO + i] = p.bo[i];
-    vecs[V_LN2G + i] = p.ln2_g[i];
-    vecs[V_LN2B + i] = p.ln2_b[i];
     vecs[V_B2 + i] = p.b2[i];
-    vecs[V_LNG + i] = p.ln_g[i];
-    vecs[V_LNB + i] = p.ln_b[i];
   }
   for (int i = threadIdx.x; i < 1024; i += kThreads) vecs[V_B1 + i] = p.b1[i];
   auto vec4 = [&](int idx, float (&o)[4]) {  // four consecutive vector elements, same address in every lane
@@ -447,20 +443,15 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = colA + c * 32 + q * 8;
-            float g8[8], b8[8], d8[8];
+            float d8[8];
             uint32_t o[4];
-            vec4(V_LN2G + col, *reinterpret_cast<float(*)[4]>(g8));
-            vec4(V_LN2G + col + 4, *reinterpret_cast<float(*)[4]>(g8 + 4));
-            vec4(V_LN2B + col, *reinterpret_cast<float(*)[4]>(b8));
-            vec4(V_LN2B + col + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
             vec4(V_B2 + col, *reinterpret_cast<float(*)[4]>(d8));
             vec4(V_B2 + col + 4, *reinterpret_cast<float(*)[4]>(d8 + 4));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint64_t xv = f2_pack(__uint_as_float(x[q * 8 + 2 * i]), __uint_as_float(x[q * 8 + 2 * i + 1]));
-              const uint64_t z = f2_fma(xv, rs2, nm2);
               float y0, y1, a0, a1;
-              f2_unpack(f2_fma(z, f2_pack(g8[2 * i], g8[2 * i + 1]), f2_pack(b8[2 * i], b8[2 * i + 1])), y0, y1);
+              f2_unpack(f2_fma(xv, rs2, nm2), y0, y1);
               o[i] = pack_bf16(y0, y1);
               f2_unpack(f2_add(xv, f2_pack(d8[2 * i], d8[2 * i + 1])), a0, a1);
               x[q * 8 + 2 * i] = __float_as_uint(a0);
@@ -615,17 +606,10 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           uint32_t (&x)[32] = c ? v2 : v;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int col = colA + c * 32 + q * 8;
-            float g8[8], b8[8];
-            vec4(V_LNG + col, *reinterpret_cast<float(*)[4]>(g8));
-            vec4(V_LNG + col + 4, *reinterpret_cast<float(*)[4]>(g8 + 4));
-            vec4(V_LNB + col, *reinterpret_cast<float(*)[4]>(b8));
-            vec4(V_LNB + col + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint64_t z = f2_fma(f2_pack(__uint_as_float(x[q * 8 + 2 * i]), __uint_as_float(x[q * 8 + 2 * i + 1])), rs2, nm2);
               float y0, y1;
-              f2_unpack(f2_fma(z, f2_pack(g8[2 * i], g8[2 * i + 1]), f2_pack(b8[2 * i], b8[2 * i + 1])), y0, y1);
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(x[q * 8 + 2 * i]), __uint_as_float(x[q * 8 + 2 * i + 1])), rs2, nm2), y0, y1);
               x[q * 4 + i] = pack_bf16(y0, y1);  // (in place: index q*4+i <= q*8+2i)
             }
           }

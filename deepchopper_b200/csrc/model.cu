@@ -215,6 +215,50 @@ static int upload_bf16(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd, 
   return DCB200_OK;
 }
 
+static int upload_f32_host(dcb200_ctx* ctx, dcb200_weights* w, const std::vector<float>& h, float** out) {
+  void* d = nullptr;
+  DCB_CUDA(cudaMalloc(&d, h.size() * 4));
+  w->allocs.push_back(d);
+  DCB_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));  // `h` is a temporary of the caller
+  *out = static_cast<float*>(d);
+  return DCB200_OK;
+}
+
+// A LayerNorm's affine part followed by a Linear is a Linear: W (z g + b) + c = (W diag(g)) z + (c + W b).  Every
+// LayerNorm of the model feeds exactly one Linear (norm1 -> in_linear, norm2 -> fc1, ln_f -> head.linear1), so the
+// kernels only normalise: 640 fewer vector elements per token row in the block kernel's epilogues.  The fold is done in
+// fp64 on the host; the folded weight is then rounded to bf16 like any other weight.
+static int upload_folded_linear(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd, const std::string& wkey,
+                                const std::string& bkey, const std::string& gkey, const std::string& betakey, int out_f,
+                                int in_f, __nv_bfloat16** w_out, float** b_out, std::vector<float>* b_host) {
+  std::vector<float> W, c, g, beta;
+  DCB_CHECK(host_copy(sd, wkey, (int64_t)out_f * in_f, W));
+  DCB_CHECK(host_copy(sd, bkey, out_f, c));
+  DCB_CHECK(host_copy(sd, gkey, in_f, g));
+  DCB_CHECK(host_copy(sd, betakey, in_f, beta));
+  for (int o = 0; o < out_f; ++o) {
+    double acc = c[o];
+    float* row = W.data() + (size_t)o * in_f;
+    for (int k = 0; k < in_f; ++k) {
+      acc += (double)row[k] * (double)beta[k];
+      row[k] = (float)((double)row[k] * (double)g[k]);
+    }
+    c[o] = (float)acc;
+  }
+  float* tmp = nullptr;
+  DCB_CHECK(upload_f32_host(ctx, w, W, &tmp));
+  void* d = nullptr;
+  DCB_CUDA(cudaMalloc(&d, W.size() * 2));
+  w->allocs.push_back(d);
+  f32_to_bf16_kernel<<<(unsigned)((W.size() + 255) / 256), 256, 0, ctx->stream>>>(tmp, static_cast<__nv_bfloat16*>(d), W.size());
+  DCB_LAUNCH_CHECK(ctx);
+  *w_out = static_cast<__nv_bfloat16*>(d);
+  DCB_CHECK(upload_f32_host(ctx, w, c, b_out));
+  if (b_host) *b_host = c;
+  return DCB200_OK;
+}
+
 int weights_destroy(dcb200_weights* w) {
   if (!w) return DCB200_OK;
   cudaSetDevice(w->device);
@@ -236,28 +280,29 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
   for (int l = 0; l < kLayers; ++l) {
     LayerW& lw = w->layer[l];
     const std::string p = "layers." + std::to_string(l) + ".";
-    DCB_CHECK(upload_bf16(ctx, w, sd, p + "mixer.in_linear.weight", 3 * kD * kD, &lw.w_in));
-    DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.in_linear.bias", 3 * kD, &lw.b_in));
+    DCB_CHECK(upload_folded_linear(ctx, w, sd, p + "mixer.in_linear.weight", p + "mixer.in_linear.bias", p + "norm1.weight",
+                                   p + "norm1.bias", 3 * kD, kD, &lw.w_in, &lw.b_in, nullptr));
     DCB_CHECK(upload_bf16(ctx, w, sd, p + "mixer.out_linear.weight", kD * kD, &lw.w_out));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.out_linear.bias", kD, &lw.b_out));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.short_filter.weight", 3 * kD * 3, &lw.short_w));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.short_filter.bias", 3 * kD, &lw.short_b));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.filter_fn.bias", kD, &lw.filt_D));
-    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm1.weight", kD, &lw.ln1_g));
-    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm1.bias", kD, &lw.ln1_b));
-    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm2.weight", kD, &lw.ln2_g));
-    DCB_CHECK(upload_f32(ctx, w, sd, p + "norm2.bias", kD, &lw.ln2_b));
-    DCB_CHECK(upload_bf16(ctx, w, sd, p + "mlp.fc1.weight", kInner * kD, &lw.w_fc1));
-    DCB_CHECK(upload_f32(ctx, w, sd, p + "mlp.fc1.bias", kInner, &lw.b_fc1));
+    // the affine parts are folded into the following Linear: what is left of each LayerNorm is the identity affine
+    // (kept for the split / FFT cross-check kernels, which still take gain and bias vectors)
+    lw.h_ln1_g.assign(kD, 1.0f);
+    lw.h_ln1_b.assign(kD, 0.0f);
+    lw.h_ln2_g.assign(kD, 1.0f);
+    lw.h_ln2_b.assign(kD, 0.0f);
+    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln1_g, &lw.ln1_g));
+    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln1_b, &lw.ln1_b));
+    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln2_g, &lw.ln2_g));
+    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln2_b, &lw.ln2_b));
+    DCB_CHECK(upload_folded_linear(ctx, w, sd, p + "mlp.fc1.weight", p + "mlp.fc1.bias", p + "norm2.weight",
+                                   p + "norm2.bias", kInner, kD, &lw.w_fc1, &lw.b_fc1, &lw.hb_fc1));
     DCB_CHECK(upload_bf16(ctx, w, sd, p + "mlp.fc2.weight", kD * kInner, &lw.w_fc2));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mlp.fc2.bias", kD, &lw.b_fc2));
-    DCB_CHECK(host_copy(sd, p + "mlp.fc1.bias", kInner, lw.hb_fc1));
     DCB_CHECK(host_copy(sd, p + "mlp.fc2.bias", kD, lw.hb_fc2));
-    DCB_CHECK(host_copy(sd, p + "norm1.weight", kD, lw.h_ln1_g));
-    DCB_CHECK(host_copy(sd, p + "norm1.bias", kD, lw.h_ln1_b));
     DCB_CHECK(host_copy(sd, p + "mixer.out_linear.bias", kD, lw.hb_out));
-    DCB_CHECK(host_copy(sd, p + "norm2.weight", kD, lw.h_ln2_g));
-    DCB_CHECK(host_copy(sd, p + "norm2.bias", kD, lw.h_ln2_b));
     // implicit filter, evaluated once for the whole positional table
     FilterW fw;
     float *z, *t, *w0, *b0, *f1, *w2, *b2, *f3, *w4, *b4, *f5, *w6, *dl;
@@ -289,12 +334,12 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_wou, lw.w_out, kD, kD, 128));
   }
-  DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.weight", kD, &w->lnf_g));
-  DCB_CHECK(upload_f32(ctx, w, sd, "ln_f.bias", kD, &w->lnf_b));
-  DCB_CHECK(host_copy(sd, "ln_f.weight", kD, w->h_lnf_g));
-  DCB_CHECK(host_copy(sd, "ln_f.bias", kD, w->h_lnf_b));
-  DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear1.weight", kInner * kD, &w->wh1));
-  DCB_CHECK(upload_f32(ctx, w, sd, "head.linear1.bias", kInner, &w->bh1));
+  w->h_lnf_g.assign(kD, 1.0f);
+  w->h_lnf_b.assign(kD, 0.0f);
+  DCB_CHECK(upload_f32_host(ctx, w, w->h_lnf_g, &w->lnf_g));
+  DCB_CHECK(upload_f32_host(ctx, w, w->h_lnf_b, &w->lnf_b));
+  DCB_CHECK(upload_folded_linear(ctx, w, sd, "head.linear1.weight", "head.linear1.bias", "ln_f.weight", "ln_f.bias", kInner,
+                                 kD, &w->wh1, &w->bh1, nullptr));
   DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear2.weight", kInner * kInner, &w->wh2));
   DCB_CHECK(upload_f32(ctx, w, sd, "head.linear2.bias", kInner, &w->bh2));
   DCB_CHECK(upload_f32(ctx, w, sd, "head.linear3.weight", 2 * kInner, &w->w3));
@@ -498,12 +543,8 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
         bp.trace = bt.as<long long>();
       }
       memcpy(bp.bo, lw.hb_out.data(), sizeof(bp.bo));
-      memcpy(bp.ln2_g, lw.h_ln2_g.data(), sizeof(bp.ln2_g));
-      memcpy(bp.ln2_b, lw.h_ln2_b.data(), sizeof(bp.ln2_b));
       memcpy(bp.b1, lw.hb_fc1.data(), sizeof(bp.b1));
       memcpy(bp.b2, lw.hb_fc2.data(), sizeof(bp.b2));
-      memcpy(bp.ln_g, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_g.data() : w->h_lnf_g.data(), sizeof(bp.ln_g));
-      memcpy(bp.ln_b, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_b.data() : w->h_lnf_b.data(), sizeof(bp.ln_b));
       // residual stream updated in place: h (hA) -> h (hA); every tile reads its rows before it writes them
       DCB_CHECK(launch_block(ctx, tm_y, lw.tm_wou, lw.tm_w1u, lw.tm_w2u, tm_hA, tm_hA, tm_u, bp));
       DCB_STAGE_DONE();

@@ -196,3 +196,28 @@ def test_forward_arbitrary_length_is_right_filled(ref, gpu):
     close("logits L=333", got, want, LOGIT_ATOL_VS_FP32, 0.0)
     lg, lab = gpu.predict_step({"input_ids": ids, "input_quals": q, "labels": torch.zeros(3, 333, dtype=torch.int8)})
     assert lg.shape == (3, 333, 2) and lab.shape == (3, 333)
+
+
+def test_forward_nontrivial_layernorm_affine():
+    """Trained checkpoints have non-trivial LayerNorm gains and biases (torch's default init is 1 / 0, which would let a
+    wrong fold of the affine parts into the following Linear go unnoticed): randomise every norm's weight and bias."""
+    from deepchopper_b200.model import DeepChopper
+    ref2 = H.make_reference_model(1)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for name, prm in ref2.named_parameters():
+            if ".norm1." in name or ".norm2." in name or ".ln_f." in name:
+                if name.endswith("weight"):
+                    prm.copy_(0.5 + torch.rand(prm.shape, generator=g))
+                else:
+                    prm.copy_(0.3 * torch.randn(prm.shape, generator=g))
+    gpu2 = DeepChopper.from_state_dict(ref2.state_dict(), device=0)
+    rng = np.random.default_rng(21)
+    for B, L in [(5, 640), (2, 2048)]:
+        ids, q = make_batch(rng, B, L)
+        with torch.no_grad():
+            want = ref2(ids, q)
+        got = gpu2(ids.cuda(), q.cuda()).cpu()
+        close(f"logits (random LayerNorm affine) L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+        decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
+        assert torch.equal((got[..., 1] > got[..., 0])[decided], (want[..., 1] > want[..., 0])[decided])
