@@ -261,27 +261,33 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           tc_fence_after();
           const uint32_t t_x0 = tmem_base + lane_off + 2 * kRegionStride + kHalo + 64 * half;
           const uint32_t obox = o_base + (2 + half) * kOutBox + row * 128;
-          if (storer) bulk_wait_read<1>();
-          bar_sync(2 + half, 128);
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            uint32_t ra[32], ha0, ha1;
-            tmem_ld32(t_x0 + 32 * sub, ra);
-            tmem_ld2(t_x0 + 32 * sub - 2, ha0, ha1);
-            tmem_ld_wait();
-            if (row_start && half == 0 && sub == 0) ha0 = ha1 = __float_as_uint(-b0);
-            sconv32_inplace(ra, ha0, ha1, w0, w1, w2, cb0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4),
-                     pack_bf16(__uint_as_float(ra[8 * q]), __uint_as_float(ra[8 * q + 1])),
-                     pack_bf16(__uint_as_float(ra[8 * q + 2]), __uint_as_float(ra[8 * q + 3])),
-                     pack_bf16(__uint_as_float(ra[8 * q + 4]), __uint_as_float(ra[8 * q + 5])),
-                     pack_bf16(__uint_as_float(ra[8 * q + 6]), __uint_as_float(ra[8 * q + 7])));
-          }
+          // The accumulator goes to registers and the region back to the MMA warp BEFORE the wait for the staging box
+          // (the previous unit's TMA store takes ~1.7 k cycles to read it): x0 of the next unit was stalling on that.
+          uint32_t ra[32], rb[32], ha0, ha1;
+          tmem_ld32(t_x0, ra);
+          tmem_ld2(t_x0 - 2, ha0, ha1);
+          tmem_ld32(t_x0 + 32, rb);
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(R_EMPTY + 2));
+          if (storer) bulk_wait_read<1>();
+          bar_sync(2 + half, 128);
+          if (row_start && half == 0) ha0 = ha1 = __float_as_uint(-b0);
+          const uint32_t hb0 = ra[30], hb1 = ra[31];  // raw values: the halo of the second 32 tokens
+          sconv32_inplace(ra, ha0, ha1, w0, w1, w2, cb0);
+          sconv32_inplace(rb, hb0, hb1, w0, w1, w2, cb0);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t (&r)[32] = sub ? rb : ra;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(obox + (((uint32_t)(sub * 4 + q) ^ sw) << 4),
+                     pack_bf16(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])),
+                     pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                     pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
+                     pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+          }
           fence_proxy_async();
           bar_sync(2 + half, 128);
           if (storer) {

@@ -97,6 +97,11 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, in
                "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() {  // <= N groups still reading their smem source
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
