@@ -14,7 +14,7 @@ EXPORTS = [
     "dcb200_weights_destroy", "dcb200_forward", "dcb200_smooth_chop", "dcb200_smooth_chop_logits",
     "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
-    "dcb200_kernel_kind_name",
+    "dcb200_kernel_kind_name", "dcb200_chop_write_bgzf",
 ]
 
 
@@ -31,6 +31,12 @@ class ChopParams(C.Structure):
         for k, v in kw.items():
             setattr(p, k, int(v))
         return p
+
+
+class FastqIndexC(C.Structure):
+    """dcb200_fastq_index."""
+    _fields_ = [("fastq", C.c_void_p), ("name_off", C.c_void_p), ("name_len", C.c_void_p), ("head_len", C.c_void_p),
+                ("seq_off", C.c_void_p), ("seq_len", C.c_void_p), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p)]
 
 
 class Dcb200Error(RuntimeError):
@@ -71,6 +77,8 @@ def lib():
     l.dcb200_kernel_kind_name.argtypes = [i32]
     l.dcb200_kernel_kind_name.restype = C.c_char_p
     pp = C.POINTER(ChopParams)
+    l.dcb200_chop_write_bgzf.argtypes = [C.POINTER(FastqIndexC), i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, C.c_char_p,
+                                         i32, i32, vp, vp]
     l.dcb200_smooth_chop.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_smooth_chop_logits.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_majority_voting.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]

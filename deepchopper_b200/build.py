@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lz"])
     return LIB
 
 

@@ -6,19 +6,17 @@ The per-read arithmetic -- argmax, drop ignored positions, majority vote, interv
 runs on the GPU (dcb200_smooth_chop_logits); the host only slices strings and writes BGZF."""
 from __future__ import annotations
 
+import ctypes as C
 import os
-import struct
-import zlib
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
 import torch
 
-from ._native import ChopParams
+from ._native import ChopParams, FastqIndexC, check, lib
 from .encode import FastqIndex, index_fastq, read_fastq_bytes
-from .smooth import (ACTION_ADAPTERS, ACTION_CHOP_I, ACTION_CHOP_T, ACTION_PASSTHROUGH, ACTION_UNCHOPPED, CHOP_TYPES, MIN_READ_LEN,
-                     id_list2seq, smooth_chop_device)
+from .smooth import CHOP_TYPES, MIN_READ_LEN, _ID_TABLE, smooth_chop_device
 from .writer import IGNORE, list_batches
 
 
@@ -30,35 +28,31 @@ class ReadResult:
     logits_ref: Tuple[int, int, int]   # (batch index, row, first column) to re-run with the FASTQ qual length
 
 
-class _BgzfWriter:
-    """Minimal BGZF (blocked gzip, htslib-compatible) writer: <=64 KiB blocks + the 28-byte EOF block."""
-    EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
-
-    def __init__(self, path: str, level: int = 6):
-        self.f = open(path, "wb")
-        self.buf = bytearray()
-        self.level = level
-
-    def write(self, data: bytes):
-        self.buf += data
-        while len(self.buf) >= 0xff00:
-            self._block(bytes(self.buf[:0xff00]))
-            del self.buf[:0xff00]
-
-    def _block(self, data: bytes):
-        c = zlib.compressobj(self.level, zlib.DEFLATED, -15)
-        comp = c.compress(data) + c.flush()
-        bsize = len(comp) + 25
-        self.f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize))
-        self.f.write(comp)
-        self.f.write(struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
-
-    def close(self):
-        if self.buf:
-            self._block(bytes(self.buf))
-            self.buf.clear()
-        self.f.write(self.EOF)
-        self.f.close()
+def write_chopped_fastq(path: str, ix: FastqIndex, has_pred: np.ndarray, pseq_ptr: np.ndarray, pseq_len: np.ndarray,
+                        action: np.ndarray, n_adapter: np.ndarray, adapter_iv: np.ndarray, n_keep: np.ndarray,
+                        keep_iv: np.ndarray, threads: int = 0, level: int = 6) -> Tuple[int, int]:
+    """dcb200_chop_write_bgzf: record assembly + BGZF on host threads (src/bin/predict.rs:266-364,
+    src/output/split.rs:60-226, src/output/writefq.rs).  All per-record arrays are in FASTQ order; ``pseq_ptr`` holds the
+    address of each record's predicted sequence bytes (kept alive by the caller).  Returns (#records, #text bytes)."""
+    R = len(ix)
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)  # noqa: E731
+    buf = c(ix.buf, np.uint8)
+    arrs = dict(name_off=c(ix.name_off, np.int64), name_len=c(ix.name_len, np.int32), head_len=c(ix.head_len, np.int32),
+                seq_off=c(ix.seq_off, np.int64), seq_len=c(ix.seq_len, np.int32), qual_off=c(ix.qual_off, np.int64),
+                qual_len=c(ix.qual_len, np.int32))
+    cix = FastqIndexC(buf.ctypes.data, *[arrs[k].ctypes.data for k in
+                                         ("name_off", "name_len", "head_len", "seq_off", "seq_len", "qual_off", "qual_len")])
+    has_pred, action = c(has_pred, np.uint8), c(action, np.uint8)
+    pseq_ptr, pseq_len = c(pseq_ptr, np.uint64), c(pseq_len, np.int32)
+    n_adapter, n_keep = c(n_adapter, np.int32), c(n_keep, np.int32)
+    adapter_iv, keep_iv = c(adapter_iv, np.int32), c(keep_iv, np.int32)
+    assert adapter_iv.ndim == 3 and keep_iv.ndim == 3 and adapter_iv.shape[0] == R and keep_iv.shape[0] == R
+    nrec, ntext = C.c_int64(0), C.c_int64(0)
+    check(lib().dcb200_chop_write_bgzf(C.byref(cix), R, has_pred.ctypes.data, pseq_ptr.ctypes.data, pseq_len.ctypes.data,
+                                       action.ctypes.data, n_adapter.ctypes.data, adapter_iv.ctypes.data,
+                                       adapter_iv.shape[1], n_keep.ctypes.data, keep_iv.ctypes.data, keep_iv.shape[1],
+                                       os.fsencode(path), int(threads), int(level), C.byref(nrec), C.byref(ntext)))
+    return int(nrec.value), int(ntext.value)
 
 
 def _read_spans(target: np.ndarray):
@@ -93,7 +87,8 @@ def load_prediction_batches(paths: Iterable[str], max_batches: Optional[int] = N
 
 
 def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None, output_prefix: Optional[str] = None,
-               max_batch_size: Optional[int] = None, device: int = 0, batches=None) -> Tuple[str, int, int]:
+               max_batch_size: Optional[int] = None, device: int = 0, batches=None, threads: int = 0,
+               level: int = 6) -> Tuple[str, int, int]:
     """src/bin/predict.rs:197-384.  Returns (output path, #predictions, #records written)."""
     params = params or ChopParams.default()
     dev = torch.device("cuda", device)
@@ -104,7 +99,19 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
     fq_ids = [ix.name(r) for r in range(len(ix))]
     qlen_of = {rid: int(ix.qual_len[r]) for r, rid in enumerate(fq_ids)}
     # ---- predictions: GPU argmax + smooth + intervals + chop coordinates per batch --------------------
-    results: Dict[str, tuple] = {}
+    R = len(ix)
+    row_of = {rid: r for r, rid in enumerate(fq_ids)}
+    approved = int(params.approved_interval_number)
+    has_pred = np.zeros(R, np.uint8)
+    action = np.zeros(R, np.uint8)
+    n_ad_all = np.zeros(R, np.int32)
+    n_keep_all = np.zeros(R, np.int32)
+    ad_all = np.zeros((R, max(1, approved), 2), np.int32)
+    keep_all = np.zeros((R, approved + 1, 2), np.int32)
+    pseq_ptr = np.zeros(R, np.uint64)
+    pseq_len = np.zeros(R, np.int32)
+    keepalive = []
+    n_pred_ids = set()
     for d in batches:
         pred = d["prediction"].float().contiguous()
         target = d["target"].to(torch.int64).numpy()
@@ -122,10 +129,30 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
             pred.to(dev), torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev), params,
             torch.from_numpy(qual_lens).to(dev), logits=True)
         n_ad, ad, n_keep, keep, act = (t.cpu().numpy() for t in (n_ad, ad, n_keep, keep, act))
-        for b in range(B):
-            s = id_list2seq(seq[b, first[b]:first[b] + lens[b]])
-            results[ids[b]] = (int(act[b]), ad[b, :n_ad[b]].tolist(), keep[b, :n_keep[b]].tolist(), s)
-    # ---- stream the FASTQ in order, assemble records -------------------------------------------------------
+        # sequence decoded from the prediction tensor (non-ACGT -> N), src/smooth/predict.rs:301
+        letters = np.ascontiguousarray(_ID_TABLE[np.where((seq >= 0) & (seq < 256), seq, 0).astype(np.uint8)])
+        keepalive.append(letters)
+        base = letters.ctypes.data
+        n_pred_ids.update(ids)
+        for b, rid in enumerate(ids):          # a later batch overrides an earlier one, like the reference's HashMap
+            r = row_of.get(rid)
+            if r is None:
+                continue
+            has_pred[r] = 1
+            action[r] = act[b]
+            n_ad_all[r] = n_ad[b]
+            n_keep_all[r] = n_keep[b]
+            ad_all[r, :ad.shape[1]] = ad[b]
+            keep_all[r, :keep.shape[1]] = keep[b]
+            pseq_ptr[r] = base + int(b) * L + int(first[b])
+            pseq_len[r] = lens[b]
+    if len(row_of) != R:                        # duplicated FASTQ ids: every occurrence gets the id's prediction
+        for r, rid in enumerate(fq_ids):
+            src = row_of[rid]
+            if src != r and has_pred[src]:
+                has_pred[r], action[r], n_ad_all[r], n_keep_all[r] = 1, action[src], n_ad_all[src], n_keep_all[src]
+                ad_all[r], keep_all[r], pseq_ptr[r], pseq_len[r] = ad_all[src], keep_all[src], pseq_ptr[src], pseq_len[src]
+    # ---- FASTQ order: assemble records + BGZF on host threads (native) --------------------------------------
     if output_prefix:
         out_dir = os.path.dirname(output_prefix) or "."
         stem = output_prefix
@@ -133,35 +160,13 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
         out_dir = os.getcwd()                                 # the reference names the output relative to the CWD
         stem = os.path.splitext(os.path.basename(fq))[0]      # Path::file_stem (src/bin/predict.rs:349)
     tmp = os.path.join(out_dir, f".deepchopper_temp_{os.getpid()}.fq.gz")
-    w = _BgzfWriter(tmp)
-    n_out = 0
-    for r, rid in enumerate(fq_ids):
-        res = results.get(rid)
-        if res is None:
-            continue                                          # no prediction -> dropped (src/bin/predict.rs:141-144)
-        act, adapters, kept, pseq = res
-        qual = ix.qual(r).decode("latin1")
-        if act == ACTION_PASSTHROUGH:
-            w.write(f"@{ix.header(r)}\n{ix.seq(r).decode('latin1')}\n+\n{qual}\n".encode("latin1"))
-            n_out += 1
-        elif act == ACTION_UNCHOPPED:
-            w.write(f"@{rid}\n{pseq}\n+\n{qual}\n".encode("latin1"))
-            n_out += 1
-        elif act == ACTION_ADAPTERS:
-            for s, e in adapters:
-                w.write(f"@{rid}|{s}:{e}\n{pseq[s:e]}\n+\n{qual[s:e]}\n".encode("latin1"))
-                n_out += 1
-        else:
-            tag = "T" if act == ACTION_CHOP_T else "I"
-            for s, e in kept:
-                w.write(f"@{rid}|{s}:{e}|{tag}\n{pseq[s:e]}\n+\n{qual[s:e]}\n".encode("latin1"))
-                n_out += 1
-    w.close()
-    out = f"{stem}.{len(results)}pd.{n_out}record.chop.fq.gz"
+    n_out, _ = write_chopped_fastq(tmp, ix, has_pred, pseq_ptr, pseq_len, action, n_ad_all, ad_all, n_keep_all, keep_all,
+                                   threads=threads, level=level)
+    out = f"{stem}.{len(n_pred_ids)}pd.{n_out}record.chop.fq.gz"
     if not output_prefix:
         out = os.path.join(os.getcwd(), out) if not os.path.isabs(out) else out
     os.replace(tmp, out)
-    return out, len(results), n_out
+    return out, len(n_pred_ids), n_out
 
 
 def params_from_cli(smooth_window=21, min_interval_size=13, approved_intervals=20, max_process_intervals=4,

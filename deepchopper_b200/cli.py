@@ -76,7 +76,8 @@ def cmd_chop(args):
     from .chop import chop_fastq, params_from_cli
     p = params_from_cli(args.smooth_window, args.min_interval_size, args.approved_intervals, args.max_process_intervals,
                         args.min_read_length, args.output_chopped, args.chop_type)
-    out, npred, nrec = chop_fastq(args.predicts, args.fq, p, args.output, args.max_batch)
+    out, npred, nrec = chop_fastq(args.predicts, args.fq, p, args.output, args.max_batch, threads=args.threads,
+                                  level=args.compression_level)
     print(f"Wrote {nrec} records to {out} ({npred} predictions)")
 
 
@@ -110,6 +111,8 @@ def build_parser():
     ch.add_argument("--output-chopped", action="store_true")
     ch.add_argument("--chop-type", default="all", choices=["terminal", "internal", "all"])
     ch.add_argument("--threads", "-t", type=int, default=2)
+    ch.add_argument("--compression-level", type=int, default=6,
+                    help="BGZF deflate level 1-9 (6 = the reference's default); 0 = Huffman-only, ~8x faster, ~5 %% larger")
     ch.add_argument("--output", "-o", default=None)
     ch.add_argument("--max-batch", type=int, default=None)
     ch.set_defaults(fn=cmd_chop)

@@ -21,6 +21,7 @@
  *                           (smooth_label_region, PyO3 src/python.rs:674-690), src/utils.rs:671-695 (get_label_region),
  *                           src/output/split.rs:60-136,171-226,260-320 and the gating of src/bin/predict.rs:137-187
  *   dcb200_smooth_chop_logits  the same after src/smooth/predict.rs:263-317 (argmax(2) + drop target == -100)
+ *   dcb200_chop_write_bgzf  src/bin/predict.rs:266-364 (write loop), src/output/split.rs:60-226, src/output/writefq.rs
  *   dcb200_predict_batch_host  the whole per-batch hot loop of `deepchopper predict` + the interval step of
  *                           `deepchopper chop` (cli.py:66-152, src/bin/predict.rs:130-192) on host buffers
  */
@@ -157,6 +158,32 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
                               const int32_t* qual_lens, int32_t R, int32_t Lpad, const dcb200_chop_params* p,
                               float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
                               int32_t* n_keep, int32_t* keep_iv, uint8_t* action);
+
+/* ---- chop output: record assembly + BGZF on host threads ---------------------------------------------
+ * Replaces the write loop of `deepchopper-chop` (src/bin/predict.rs:266-364), the record naming / slicing of
+ * src/output/split.rs:60-226 and the bgzf writer of src/output/writefq.rs.  No GPU work: the per-read decisions are the
+ * outputs of dcb200_smooth_chop* (action, adapter_iv [R,adapter_stride,2], keep_iv [R,keep_stride,2]).
+ * Records are visited in FASTQ order; has_pred[r] == 0 drops the record (no prediction for it).  pseq[r] / pseq_len[r]
+ * is the sequence decoded from the prediction batch (src/smooth/predict.rs:301: tokens -> ACGTN), used for every
+ * action but PASSTHROUGH, which copies the FASTQ record verbatim (header with description, sequence, quality).
+ * threads <= 0: all host cores; level 1-9 = zlib levels, 0 = Huffman-only deflate (about 8x the speed of level 6 for
+ * ~5 % more bytes on FASTQ text), anything else = 6.  The file is a valid BGZF (htslib) stream whose decompressed
+ * bytes do not depend on `threads`. */
+typedef struct dcb200_fastq_index {
+  const uint8_t* fastq;      /* the whole FASTQ text */
+  const int64_t* name_off;   /* [R] offset of the byte after '@' */
+  const int32_t* name_len;   /* [R] id length (up to the first blank) */
+  const int32_t* head_len;   /* [R] full header line length after '@' */
+  const int64_t* seq_off;    /* [R] */
+  const int32_t* seq_len;    /* [R] */
+  const int64_t* qual_off;   /* [R] */
+  const int32_t* qual_len;   /* [R] */
+} dcb200_fastq_index;
+int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, const uint8_t* has_pred,
+                           const uint8_t* const* pseq, const int32_t* pseq_len, const uint8_t* action,
+                           const int32_t* n_adapter, const int32_t* adapter_iv, int32_t adapter_stride,
+                           const int32_t* n_keep, const int32_t* keep_iv, int32_t keep_stride, const char* path,
+                           int32_t threads, int32_t level, int64_t* n_records, int64_t* n_text_bytes);
 
 /* ---- diagnostics (used by the parity tests to localise a mismatch) ---------------------------------
  * dcb200_forward_debug == dcb200_forward that stops after `stop_stage` kernels of the forward chain
