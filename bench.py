@@ -59,11 +59,14 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}
 
 
-def synth_workload(n_reads: int, seed: int):
+def synth_workload(n_reads: int, seed: int, workload: str = "configs1"):
     """Synthetic dRNA-like reads as one byte blob [all seq strings | all quality strings]."""
     from deepchopper_b200 import synth
     rng = np.random.default_rng(seed)
-    lens = synth.read_lengths(rng, n_reads, hi=8000)
+    if workload == "stress":   # BASELINE configs[3]: 16-32 kb reads (not the headline; `--workload stress`)
+        lens = rng.integers(16384, 32767, n_reads).astype(np.int64)
+    else:
+        lens = synth.read_lengths(rng, n_reads, hi=8000)
     total = int(lens.sum())
     seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, total, dtype=np.uint8)]
     seq[rng.random(total, dtype=np.float32) < 0.001] = ord("N")
@@ -238,7 +241,7 @@ def run_ours(args, rank, local, world):
     peaks = load_peaks()
     sd = random_state_dict(0)
     model = DeepChopper.from_state_dict(sd, device=dev)
-    blob, seq_off, qual_off, lens = synth_workload(args.reads, args.seed + 1000 * rank)
+    blob, seq_off, qual_off, lens = synth_workload(args.reads, args.seed + 1000 * rank, args.workload)
     batches = plan_batches(lens, token_budget=args.token_budget)
     bases = int(lens.sum())
     padded_tokens = int(sum(b.rows.size * b.Lrow for b in batches))
@@ -344,8 +347,11 @@ def run_ours(args, rank, local, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {args.reads} synthetic reads per GPU, log-normal length (median 1 kb, "
-                               "clipped to [200, 8000]), random-init HyenaDNA-small-32k + DeepChopper head",
+        "config": {"workload": (f"configs[1]: {args.reads} synthetic reads per GPU, log-normal length (median 1 kb, "
+                                "clipped to [200, 8000]), random-init HyenaDNA-small-32k + DeepChopper head"
+                                if args.workload == "configs1" else
+                                f"configs[3] long-read stress: {args.reads} synthetic reads per GPU, length U[16384, 32766], "
+                                "random-init HyenaDNA-small-32k + DeepChopper head"),
                    "batching": f"length-bucketed, <= {args.token_budget} padded tokens per batch, left-pad to batch max",
                    "batches_per_step": len(batches), "l2": "inputs_larger_than_l2", "parallelism": f"read-sharded x{world}"},
         "reads_per_sec": reads_all * args.steps / (ms_total / 1e3),
@@ -380,6 +386,8 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=192)
     ap.add_argument("--ref-reads", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "stress"],
+                    help="configs1 = BASELINE configs[1] (the headline); stress = configs[3], 16-32 kb reads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -34,9 +34,12 @@ class Batch:
 
 
 def plan_batches(lens: np.ndarray, token_budget: int = 1024 * 1024, max_rows: int = 8192,
-                 sort: bool = True) -> List[Batch]:
+                 sort: bool = True, long_read_cap: int = 128 * 32768) -> List[Batch]:
     """Length-bucketed batches of ~token_budget padded tokens.  ``sort=False`` keeps FASTQ order
-    (the reference's own batching when combined with a fixed ``max_rows``)."""
+    (the reference's own batching when combined with a fixed ``max_rows``).  For reads so long that the budget holds
+    fewer than 128 of them the budget stretches to one full 128-row tile (at most ``long_read_cap`` tokens, ~25 GB of
+    activations): the long convolution's MMAs have the batch rows as their M dimension, and a 32-row batch of 32 kb
+    reads would spend 3/4 of them on nothing."""
     lens = np.minimum(np.asarray(lens, dtype=np.int64), MAX_TOKENS - 1)
     order = np.argsort(lens, kind="stable") if sort else np.arange(lens.size)
     batches: List[Batch] = []
@@ -48,7 +51,8 @@ def plan_batches(lens: np.ndarray, token_budget: int = 1024 * 1024, max_rows: in
         while j < n and (j - i) < max_rows:
             m2 = max(mx, int(lens[order[j]]))
             lrow = (m2 + 1 + ROW_TILE - 1) // ROW_TILE * ROW_TILE
-            if j > i and (j - i + 1) * lrow > token_budget:
+            budget = max(token_budget, min(ROW_TILE * lrow, long_read_cap)) if sort else token_budget
+            if j > i and (j - i + 1) * lrow > budget:
                 break
             mx = m2
             j += 1

@@ -23,8 +23,15 @@ def test_plan_batches_covers_every_read_once():
     assert np.array_equal(np.sort(seen), np.arange(lens.size))
     for b in bs:
         assert b.Lpad == lens[b.rows].max() + 1 and b.Lrow % 128 == 0 and b.Lrow >= b.Lpad
-        # the token budget is soft: row counts are rounded to full 128-row tiles (x4 when large), at most 1.3 x budget
-        assert b.rows.size == 1 or b.rows.size * b.Lrow <= 1.3 * 256 * 1024
+        # the token budget is soft: row counts are rounded to full 128-row tiles (x4 when large), at most 1.3 x budget;
+        # reads too long for 128 of them to fit get exactly one full row tile (the conv kernel's M dimension)
+        assert b.rows.size <= 128 or b.rows.size * b.Lrow <= 1.3 * 256 * 1024
+    strict = plan_batches(lens, token_budget=256 * 1024, long_read_cap=0)
+    assert all(b.rows.size == 1 or b.rows.size * b.Lrow <= 1.3 * 256 * 1024 for b in strict)
+    long_lens = rng.integers(16384, 32767, 300)
+    lb = plan_batches(long_lens)
+    assert np.array_equal(np.sort(np.concatenate([b.rows for b in lb])), np.arange(300))
+    assert all(b.rows.size == 128 for b in lb[:-1]) and max(b.rows.size * b.Lrow for b in lb) <= 128 * 32768
     # reference batching: FASTQ order, fixed rows
     fb = plan_batches(lens, token_budget=1 << 62, max_rows=12, sort=False)
     assert all(np.array_equal(b.rows, np.arange(i * 12, min(lens.size, (i + 1) * 12))) for i, b in enumerate(fb))
