@@ -21,6 +21,8 @@
 #include "inproj.h"
 #include "ptx.cuh"
 
+#include <string.h>
+
 namespace dcb {
 
 using namespace ptx;
@@ -33,6 +35,8 @@ constexpr int kHalo = 16;
 constexpr uint32_t kUBox = kN * 128;          // 18 KB: 144 token rows x 64 k
 constexpr uint32_t kWBox = 128 * 128;         // 16 KB: 128 channel rows x 64 k
 constexpr int kWStages = 4;
+constexpr int kCluster = 2;                   // CTAs that share every weight box through a multicast TMA load
+constexpr uint32_t kWSlice = kWBox / kCluster;  // the rows of a box that one CTA fetches for the whole cluster
 constexpr uint32_t kOutBox = 128 * 128;       // 16 KB: 128 channel rows x 64 tokens (bf16)
 constexpr int kRegionStride = 160;
 
@@ -96,7 +100,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     }
     for (int s = 0; s < kWStages; ++s) {
       mbar_init(bar(W_FULL + s), 1);
-      mbar_init(bar(W_EMPTY + s), 1);
+      mbar_init(bar(W_EMPTY + s), kCluster);  // every CTA of the cluster has read the stage
     }
     for (int s = 0; s < 3; ++s) {
       mbar_init(bar(R_FULL + s), 1);
@@ -118,9 +122,22 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // the peers' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int num_tiles = p.num_tiles;
+  // The CTAs of a cluster walk DIFFERENT token tiles through the same (series, channel group, k box) sequence in
+  // lockstep: every weight box is read from L2 once per cluster (each CTA fetches 1/kCluster of its rows and multicasts
+  // them).  Weights were 2/3 of what this kernel pulls through L2 (3 KB of the 4.5 KB per token).  A cluster whose last
+  // round has fewer tiles than CTAs repeats the last tile (identical bytes are stored twice).
+  const uint32_t crank = cluster_ctarank();
+  const int n_rounds = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int first = (int)(blockIdx.x / kCluster) * kCluster + (int)crank;   // == blockIdx.x
+  auto tile_of = [&](int round) {
+    const int o = first + round * (int)gridDim.x;
+    return o < num_tiles ? o : num_tiles - 1;
+  };
+  constexpr uint16_t kMask = (1u << kCluster) - 1;
 
   // series order within a unit (token tile, channel group g): x1, v, x0  ->  TMEM region = series index
   // W_in row offset of series s for group g: x1 -> 256, v -> 512, x0 -> 0   (+ 128 g)
@@ -129,8 +146,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t wphase = 0, n = 0;
-      for (int o = blockIdx.x; o < num_tiles; o += gridDim.x, ++n) {
-        const int tok0 = o * 128;
+      for (int rd = 0; rd < n_rounds; ++rd, ++n) {
+        const int tok0 = tile_of(rd) * 128;
         for (int g = 0; g < 2; ++g) {
           for (int s = 0; s < 3; ++s) {
             const int wrow = (s == 0 ? 256 : (s == 1 ? 512 : 0)) + 128 * g;
@@ -142,7 +159,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
               }
               mbar_wait(bar(W_EMPTY + stage), wphase ^ 1);
               mbar_arrive_expect_tx(bar(W_FULL + stage), kWBox);
-              tma_load_2d(w_base + stage * kWBox, &tmW, bar(W_FULL + stage), kb * 64, wrow);
+              tma_load_2d_mc(w_base + stage * kWBox + crank * kWSlice, &tmW, bar(W_FULL + stage), kb * 64,
+                             wrow + (int)crank * (128 / kCluster), kMask);
               if (++stage == kWStages) {
                 stage = 0;
                 wphase ^= 1;
@@ -153,13 +171,14 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, the elected lane issues (see ptx.cuh elect_one) =====
+    {
+      const uint32_t el = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_bf16(128, kN, false, false);
       int stage = 0;
       uint32_t wphase = 0, n = 0;
       uint32_t use = 0;  // units started (each region is used once per unit)
-      for (int o = blockIdx.x; o < num_tiles; o += gridDim.x, ++n) {
+      for (int rd = 0; rd < n_rounds; ++rd, ++n) {
         for (int g = 0; g < 2; ++g, ++use) {
           for (int s = 0; s < 3; ++s) {
             mbar_wait(bar(R_EMPTY + s), (use & 1) ^ 1);
@@ -171,15 +190,15 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
               tc_fence_after();
               const uint32_t a_addr = w_base + stage * kWBox;
               const uint32_t b_addr = u_base + kb * kUBox;
-              umma_bf16_x4<1>(d, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kb ? 1u : 0u);
-              umma_commit(bar(W_EMPTY + stage));
-              if (g == 1 && s == 2) umma_commit(bar(U_EMPTY + kb));  // last series of the tile: u box kb may be refilled
+              umma_bf16_x4_e<1>(d, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kb ? 1u : 0u, el);
+              umma_commit_mc_e(bar(W_EMPTY + stage), kMask, el);
+              if (g == 1 && s == 2) umma_commit_e(bar(U_EMPTY + kb), el);  // last series of the tile: u box kb may be refilled
               if (++stage == kWStages) {
                 stage = 0;
                 wphase ^= 1;
               }
             }
-            umma_commit(bar(R_FULL + s));
+            umma_commit_e(bar(R_FULL + s), el);
           }
         }
       }
@@ -193,8 +212,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const bool storer = (quad == 0 && lane == 0);  // one per half
     uint32_t use = 0;
-    for (int o = blockIdx.x; o < num_tiles; o += gridDim.x) {
-      const int tok0 = o * 128;
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const int tok0 = tile_of(rd) * 128;
       const int b = tok0 / p.L, l0 = tok0 % p.L;
       const bool row_start = (l0 == 0);  // conv zero padding: the halo columns then hold the previous read's tail
       for (int g = 0; g < 2; ++g, ++use) {
@@ -302,6 +321,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // a peer may still be multicasting into my ring / signalling my barriers until here
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -312,10 +332,25 @@ int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorM
                        const CUtensorMap& tm_gate, const InprojParams& p) {
   const size_t smem = 4 * kUBox + kWStages * kWBox + 4 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&inproj_conv_kernel), smem));
-  const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  int clusters = ctx->sm_count / kCluster;
+  const int want = (p.num_tiles + kCluster - 1) / kCluster;
+  if (want < clusters) clusters = want;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(kCluster * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   ProfScope prof(ctx, K_INPROJ);
-  inproj_conv_kernel<<<grid, kThreads, smem, ctx->stream>>>(tm_u, tm_w, tm_vv, tm_gate, p);
-  DCB_LAUNCH_CHECK(ctx);
+  DCB_CUDA(cudaLaunchKernelEx(&cfg, inproj_conv_kernel, tm_u, tm_w, tm_vv, tm_gate, p));
+  ctx->launches++;
   return DCB200_OK;
 }
 

@@ -34,7 +34,7 @@ struct LayerW {
   float* k = nullptr;  // [256][Lmax] implicit filter, evaluated once
   std::map<int, float2*> KF;  // per FFT size N: [256][N]
   __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
-  CUtensorMap tm_in, tm_out;
+  CUtensorMap tm_in, tm_in_mc, tm_out;
   std::vector<float> hb_fc1, hb_fc2, h_ln1_g, h_ln1_b, hb_out, h_ln2_g, h_ln2_b;  // host copies: passed to kernels as constant-bank parameters
   CUtensorMap tm_w1u, tm_w2u, tm_wou;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
 };
@@ -329,6 +329,7 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     implicit_filter_kernel<<<(w->Lmax + 127) / 128, 128, 0, ctx->stream>>>(fw, w->Lmax, lw.k);
     DCB_LAUNCH_CHECK(ctx);
     DCB_CHECK(make_tmap_2d(&lw.tm_in, lw.w_in, 3 * kD, kD, 128));
+    DCB_CHECK(make_tmap_2d(&lw.tm_in_mc, lw.w_in, 3 * kD, kD, 64));  // inproj_conv: half boxes, multicast across a cluster of 2
     DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
@@ -506,7 +507,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       ip.b_in = lw.b_in;
       ip.short_w = lw.short_w;
       ip.short_b = lw.short_b;
-      DCB_CHECK(launch_inproj_conv(ctx, tm_u144, lw.tm_in, tm_vv_st, tm_gate_st, ip));
+      DCB_CHECK(launch_inproj_conv(ctx, tm_u144, lw.tm_in_mc, tm_vv_st, tm_gate_st, ip));
       DCB_STAGE_DONE();
       DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, w->toep_cap, tm_vv, tm_gate, tm_yr, B, L));
     } else {

@@ -65,6 +65,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Multicast load: the box lands at the same shared-memory offset in every CTA of `mask`, and each of those CTAs gets the
+// complete_tx on its own barrier at the same offset: one L2 read feeds the whole cluster.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -137,6 +145,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (a stage shared by a cluster through multicast
+// loads is free once every CTA's MMAs have read it)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // 32 lanes x 32 columns of 32-bit: thread i of the warp gets lane (32*(warp%4)+i), columns c..c+31
@@ -296,6 +311,76 @@ __device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint64_t a0, uint3
         "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first)
         : "memory");
   }
+}
+
+// ---- warp-converged issue: the whole MMA warp runs the issue loop (so ptxas keeps barrier addresses and descriptors in
+// uniform registers instead of moving them there with R2UR / ELECT waterfall loops inside a one-lane branch: ~70 dependent
+// instructions per 4 MMAs, ~120 cycles per MMA, which bounds MMAs smaller than N = 256) and only the tcgen05 instructions
+// themselves are predicated on the elected lane.
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_bf16_x4_e(uint32_t tmem_d, uint64_t a0, uint32_t a_inc, uint64_t b0, uint32_t b_inc,
+                                               uint32_t idesc, uint32_t accumulate_first, uint32_t elected) {
+  const uint64_t a1 = a0 + a_inc, a2 = a0 + 2 * a_inc, a3 = a0 + 3 * a_inc;
+  const uint64_t b1 = b0 + b_inc, b2 = b0 + 2 * b_inc, b3 = b0 + 3 * b_inc;
+  if (kCtaGroup == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1, pe;\n"
+        "setp.ne.b32 p0, %10, 0;\n"
+        "setp.eq.b32 p1, %10, %10;\n"
+        "setp.ne.b32 pe, %11, 0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %5, %9, p0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %6, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %7, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %8, %9, p1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first), "r"(elected)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1, pe;\n"
+        "setp.ne.b32 p0, %10, 0;\n"
+        "setp.eq.b32 p1, %10, %10;\n"
+        "setp.ne.b32 pe, %11, 0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %5, %9, p0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %6, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %7, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %4, %8, %9, p1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate_first), "r"(elected)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "setp.ne.b32 pe, %1, 0;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar),
+      "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_e(uint32_t bar, uint16_t mask, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "setp.ne.b32 pe, %2, 0;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "h"(mask), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_e(uint32_t bar, uint16_t mask, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "setp.ne.b32 pe, %2, 0;\n"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "h"(mask), "r"(elected)
+      : "memory");
 }
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: half the issue slots of scalar fp32) -------
