@@ -199,15 +199,16 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader only) =====
-    if (lane == 0 && leader) {
+    // ===== MMA issuer (leader only): the whole warp runs the loop, the elected lane issues (ptx.cuh umma_bf16_x4_e) =====
+    if (leader) {
+      const uint32_t el = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc2 = make_idesc_bf16(256, 256, false, false);
       int slot = 0;
       uint32_t wphase = 0;
       uint32_t n = 0;   // tile pairs done by this cluster
       uint32_t t1 = 0;  // uses of acc1 started so far (out_proj + 4 fc1 groups per tile)
       constexpr uint32_t idesc_o = make_idesc_bf16(256, 256, true, false);  // A = y tile, MN-major
-      TracerT<kTrace> tr{traced ? p.trace : nullptr, 0};
+      TracerT<kTrace> tr{(traced && el) ? p.trace : nullptr, 0};
       auto advance = [&]() {
         if (++slot == kSlots) {
           slot = 0;
@@ -231,12 +232,12 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             tc_fence_after();
             const uint32_t a_addr = a_base + kb * kUnitBytes;
             const uint32_t b_addr = w_base + slot * kUnitBytes;
-            umma_bf16_x4<2>(d, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc2, kb ? 1u : 0u);
-            umma_commit_2sm(bar(W_EMPTY + slot), 3);
+            umma_bf16_x4_e<2>(d, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc2, kb ? 1u : 0u, el);
+            umma_commit_2sm_e(bar(W_EMPTY + slot), 3, el);
             advance();
           }
-          umma_commit_2sm(bar(T1_FULL), 3);
-          if (P == kChunks - 1) umma_commit_2sm(bar(A_EMPTY), 3);
+          umma_commit_2sm_e(bar(T1_FULL), 3, el);
+          if (P == kChunks - 1) umma_commit_2sm_e(bar(A_EMPTY), 3, el);
         };
         auto fc2 = [&](int j) {
           tr(200 + j);
@@ -251,13 +252,13 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             tc_fence_after();
             const uint32_t a_addr = g_base + kb * kUnitBytes;
             const uint32_t b_addr = w_base + slot * kUnitBytes;
-            umma_bf16_x4<2>(tmem_base, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc2,
-                            1u);  // acc2 was preloaded with x1 + b2 by epilogue O
-            umma_commit_2sm(bar(W_EMPTY + slot), 3);
+            umma_bf16_x4_e<2>(tmem_base, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc2,
+                              1u, el);  // acc2 was preloaded with x1 + b2 by epilogue O
+            umma_commit_2sm_e(bar(W_EMPTY + slot), 3, el);
             advance();
           }
-          umma_commit_2sm(bar(G_EMPTY), 3);
-          if (j == kChunks - 1) umma_commit_2sm(bar(T2_FULL), 3);
+          umma_commit_2sm_e(bar(G_EMPTY), 3, el);
+          if (j == kChunks - 1) umma_commit_2sm_e(bar(T2_FULL), 3, el);
         };
         tr(90);
         mbar_wait(bar(A_FULL), n & 1);
@@ -272,13 +273,13 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t a_addr = a_base + kc * kUnitBytes;  // [tokens 0-63 | tokens 64-127] x 64 channels, 8 KB each
           const uint32_t b_addr = w_base + slot * kUnitBytes;
-          umma_bf16_x4<2>(tmem_base + 256, make_desc_sw128(a_addr, 8192, 1024), 128, make_desc_sw128(b_addr, 16, 1024), 2, idesc_o,
-                          kc ? 1u : 0u);
-          umma_commit_2sm(bar(W_EMPTY + slot), 3);
+          umma_bf16_x4_e<2>(tmem_base + 256, make_desc_sw128(a_addr, 8192, 1024), 128, make_desc_sw128(b_addr, 16, 1024), 2,
+                            idesc_o, kc ? 1u : 0u, el);
+          umma_commit_2sm_e(bar(W_EMPTY + slot), 3, el);
           advance();
         }
-        umma_commit_2sm(bar(T1_FULL), 3);
-        umma_commit_2sm(bar(Y_DEAD), 3);
+        umma_commit_2sm_e(bar(T1_FULL), 3, el);
+        umma_commit_2sm_e(bar(Y_DEAD), 3, el);
         tr(92);
         mbar_wait_cluster(bar(M_FULL), n & 1);  // m tile written over the y tile, acc2 preloaded (both CTAs)
         tr(93);
