@@ -154,8 +154,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, the elected lane issues (ptx.cuh umma_bf16_x4_e) =====
+    {
+      const uint32_t el = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, NT, Tr::A_MN, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -174,14 +175,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t b_addr = a_addr + A_BYTES;
             // K-major tiles advance 32 B per K = 16 slice; the MN-major A tile (out_proj) 2 KB per slice
             const uint64_t adesc0 = Tr::A_MN ? make_desc_sw128(a_addr, 8192, 1024) : make_desc_sw128(a_addr, 16, 1024);
-            umma_bf16_x4<1>(d_tmem, adesc0, Tr::A_MN ? 128 : 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kc ? 1u : 0u);
-            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            umma_bf16_x4_e<1>(d_tmem, adesc0, Tr::A_MN ? 128 : 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kc ? 1u : 0u, el);
+            umma_commit_e(empty_bar(stage), el);  // frees the smem slot once these MMAs retire
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          umma_commit_e(tfull_bar(acc), el);  // accumulator complete -> epilogue
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;

@@ -67,6 +67,7 @@ __device__ __forceinline__ void sconv32_inplace(uint32_t (&r)[32], uint32_t h0, 
 
 }  // namespace
 
+template <bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmVV, const __grid_constant__ CUtensorMap tmGate,
@@ -138,6 +139,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     return o < num_tiles ? o : num_tiles - 1;
   };
   constexpr uint16_t kMask = (1u << kCluster) - 1;
+  const bool traced = kTrace && p.trace != nullptr && blockIdx.x == 0;
 
   // series order within a unit (token tile, channel group g): x1, v, x0  ->  TMEM region = series index
   // W_in row offset of series s for group g: x1 -> 256, v -> 512, x0 -> 0   (+ 128 g)
@@ -174,6 +176,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     // ===== MMA issuer: the whole warp runs the loop, the elected lane issues (see ptx.cuh elect_one) =====
     {
       const uint32_t el = elect_one() ? 1u : 0u;
+      TracerT<kTrace> tr{(traced && el) ? p.trace : nullptr, 0};
       constexpr uint32_t idesc = make_idesc_bf16(128, kN, false, false);
       int stage = 0;
       uint32_t wphase = 0, n = 0;
@@ -181,12 +184,15 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
       for (int rd = 0; rd < n_rounds; ++rd, ++n) {
         for (int g = 0; g < 2; ++g, ++use) {
           for (int s = 0; s < 3; ++s) {
+            tr(90 + s);
             mbar_wait(bar(R_EMPTY + s), (use & 1) ^ 1);
+            tr(100 + s);
             tc_fence_after();
             const uint32_t d = tmem_base + s * kRegionStride;
             for (int kb = 0; kb < 4; ++kb) {
               if (g == 0 && s == 0) mbar_wait(bar(U_FULL + kb), n & 1);
               mbar_wait(bar(W_FULL + stage), wphase);
+              tr(120 + s);
               tc_fence_after();
               const uint32_t a_addr = w_base + stage * kWBox;
               const uint32_t b_addr = u_base + kb * kUBox;
@@ -212,6 +218,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const bool storer = (quad == 0 && lane == 0);  // one per half
     uint32_t use = 0;
+    TracerT<kTrace> tr{(traced && warp == 4 && lane == 0) ? p.trace + 2 * kTraceCap : nullptr, 0};
     for (int rd = 0; rd < n_rounds; ++rd) {
       const int tok0 = tile_of(rd) * 128;
       const int b = tok0 / p.L, l0 = tok0 % p.L;
@@ -224,8 +231,10 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           const float* cv = cst + (512 + ch) * 5;
           const float b1 = c1[0], w10 = c1[1], w11 = c1[2], w12 = c1[3], cb1 = fmaf(c1[0], (c1[1] + c1[2]) + c1[3], c1[4]);
           const float bv = cv[0], wv0 = cv[1], wv1 = cv[2], wv2 = cv[3], cbv = fmaf(cv[0], (cv[1] + cv[2]) + cv[3], cv[4]);
+          tr(400);
           mbar_wait(bar(R_FULL + 0), use & 1);
           mbar_wait(bar(R_FULL + 1), use & 1);
+          tr(410);
           tc_fence_after();
           const uint32_t t_x1 = tmem_base + lane_off + 0 * kRegionStride + kHalo + 64 * half;
           const uint32_t t_v = tmem_base + lane_off + 1 * kRegionStride + kHalo + 64 * half;
@@ -233,6 +242,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           // wait until the previous unit's store from this box has finished reading it
           if (storer) bulk_wait_read<1>();
           bar_sync(2 + half, 128);
+          tr(420);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             uint32_t ra[32], rb[32], ha0, ha1, hb0, hb1;
@@ -265,6 +275,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             mbar_arrive(bar(R_EMPTY + 0));
             mbar_arrive(bar(R_EMPTY + 1));
           }
+          tr(430);
           fence_proxy_async();
           bar_sync(2 + half, 128);
           if (storer) {
@@ -276,7 +287,9 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         {
           const float* c0 = cst + ch * 5;
           const float b0 = c0[0], w0 = c0[1], w1 = c0[2], w2 = c0[3], cb0 = fmaf(c0[0], (c0[1] + c0[2]) + c0[3], c0[4]);
+          tr(440);
           mbar_wait(bar(R_FULL + 2), use & 1);
+          tr(450);
           tc_fence_after();
           const uint32_t t_x0 = tmem_base + lane_off + 2 * kRegionStride + kHalo + 64 * half;
           const uint32_t obox = o_base + (2 + half) * kOutBox + row * 128;
@@ -290,8 +303,10 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(R_EMPTY + 2));
+          tr(460);
           if (storer) bulk_wait_read<1>();
           bar_sync(2 + half, 128);
+          tr(470);
           if (row_start && half == 0) ha0 = ha1 = __float_as_uint(-b0);
           const uint32_t hb0 = ra[30], hb1 = ra[31];  // raw values: the halo of the second 32 tokens
           sconv32_inplace(ra, ha0, ha1, w0, w1, w2, cb0);
@@ -313,6 +328,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             tma_store_3d(&tmGate, o_base + (2 + half) * kOutBox, l0 + 64 * half, g * 128, b);
             bulk_commit();
           }
+          tr(480);
         }
       }
     }
@@ -331,7 +347,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorMap& tm_w, const CUtensorMap& tm_vv,
                        const CUtensorMap& tm_gate, const InprojParams& p) {
   const size_t smem = 4 * kUBox + kWStages * kWBox + 4 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
-  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&inproj_conv_kernel), smem));
+  auto kern = p.trace ? &inproj_conv_kernel<true> : &inproj_conv_kernel<false>;
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(kern), smem));
   int clusters = ctx->sm_count / kCluster;
   const int want = (p.num_tiles + kCluster - 1) / kCluster;
   if (want < clusters) clusters = want;
@@ -349,7 +366,7 @@ int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorM
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(ctx, K_INPROJ);
-  DCB_CUDA(cudaLaunchKernelEx(&cfg, inproj_conv_kernel, tm_u, tm_w, tm_vv, tm_gate, p));
+  DCB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_u, tm_w, tm_vv, tm_gate, p));
   ctx->launches++;
   return DCB200_OK;
 }

@@ -507,6 +507,13 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       ip.b_in = lw.b_in;
       ip.short_w = lw.short_w;
       ip.short_b = lw.short_b;
+      ip.trace = nullptr;
+      if (l == 0 && getenv("DCB200_TRACE") && !strcmp(getenv("DCB200_TRACE"), "inproj")) {
+        DevBuf& bt = ctx->buf("trace");
+        DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
+        DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
+        ip.trace = bt.as<long long>();
+      }
       DCB_CHECK(launch_inproj_conv(ctx, tm_u144, lw.tm_in_mc, tm_vv_st, tm_gate_st, ip));
       DCB_STAGE_DONE();
       DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, w->toep_cap, tm_vv, tm_gate, tm_yr, B, L));

@@ -153,8 +153,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, the elected lane issues (ptx.cuh umma_bf16_x4_e) =====
+    {
+      const uint32_t el = elect_one() ? 1u : 0u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
@@ -174,16 +175,16 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
               tc_fence_after();
               const uint32_t a_addr = a_base + stage * kTzStage;
               // A: +32 B per K = 16 slice inside the swizzled tile; B: the window slides by two core matrices (256 B)
-              umma_bf16_x4<1>(d_tmem, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_nosw(a_addr + kTzBox, 128, 128), 16, idesc,
-                              (i | hh) ? 1u : 0u);
-              umma_commit(aempty(stage));
+              umma_bf16_x4_e<1>(d_tmem, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_nosw(a_addr + kTzBox, 128, 128), 16, idesc,
+                              (i | hh) ? 1u : 0u, el);
+              umma_commit_e(aempty(stage), el);
               if (++stage == kTzAStages) {
                 stage = 0;
                 phase ^= 1;
               }
             }
           }
-          umma_commit(tfull(acc));
+          umma_commit_e(tfull(acc), el);
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
