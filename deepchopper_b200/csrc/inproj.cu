@@ -144,21 +144,16 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   // series order within a unit (token tile, channel group g): x1, v, x0  ->  TMEM region = series index
   // W_in row offset of series s for group g: x1 -> 256, v -> 512, x0 -> 0   (+ 128 g)
   if (warp == 0) {
-    // ===== producer =====
+    // ===== weight producer =====  (the u boxes have their own loader, warp 3: waiting here for a u box of the previous
+    // tile to retire kept the weight ring from running ahead across the tile boundary, ~3 k cycles per tile)
     if (lane == 0) {
       int stage = 0;
-      uint32_t wphase = 0, n = 0;
-      for (int rd = 0; rd < n_rounds; ++rd, ++n) {
-        const int tok0 = tile_of(rd) * 128;
+      uint32_t wphase = 0;
+      for (int rd = 0; rd < n_rounds; ++rd) {
         for (int g = 0; g < 2; ++g) {
           for (int s = 0; s < 3; ++s) {
             const int wrow = (s == 0 ? 256 : (s == 1 ? 512 : 0)) + 128 * g;
             for (int kb = 0; kb < 4; ++kb) {
-              if (g == 0 && s == 0) {  // this tile's u box kb (its previous content retired with the last series)
-                mbar_wait(bar(U_EMPTY + kb), (n & 1) ^ 1);
-                mbar_arrive_expect_tx(bar(U_FULL + kb), kUBox);
-                tma_load_2d(u_base + kb * kUBox, &tmU, bar(U_FULL + kb), kb * 64, tok0 - kHalo);
-              }
               mbar_wait(bar(W_EMPTY + stage), wphase ^ 1);
               mbar_arrive_expect_tx(bar(W_FULL + stage), kWBox);
               tma_load_2d_mc(w_base + stage * kWBox + crank * kWSlice, &tmW, bar(W_FULL + stage), kb * 64,
@@ -206,6 +201,19 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
             }
             umma_commit_e(bar(R_FULL + s), el);
           }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== u-tile loader: box kb of the next tile as soon as the tile's last series has retired its k block kb =====
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int rd = 0; rd < n_rounds; ++rd, ++n) {
+        const int tok0 = tile_of(rd) * 128;
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(bar(U_EMPTY + kb), (n & 1) ^ 1);
+          mbar_arrive_expect_tx(bar(U_FULL + kb), kUBox);
+          tma_load_2d(u_base + kb * kUBox, &tmU, bar(U_FULL + kb), kb * 64, tok0 - kHalo);
         }
       }
     }
