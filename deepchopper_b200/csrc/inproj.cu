@@ -207,6 +207,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   } else if (warp == 3) {
     // ===== u-tile loader: box kb of the next tile as soon as the tile's last series has retired its k block kb =====
     if (lane == 0) {
+      // u comes from HBM (the previous kernel wrote 0.5 GB of it): an L2 prefetch one tile ahead turns the 4-5 k cycle
+      // wait of the tile's first series into an L2 hit
       uint32_t n = 0;
       for (int rd = 0; rd < n_rounds; ++rd, ++n) {
         const int tok0 = tile_of(rd) * 128;
@@ -214,6 +216,10 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           mbar_wait(bar(U_EMPTY + kb), (n & 1) ^ 1);
           mbar_arrive_expect_tx(bar(U_FULL + kb), kUBox);
           tma_load_2d(u_base + kb * kUBox, &tmU, bar(U_FULL + kb), kb * 64, tok0 - kHalo);
+        }
+        if (rd + 1 < n_rounds) {
+          const int nxt = tile_of(rd + 1) * 128;
+          for (int kb = 0; kb < 4; ++kb) tma_prefetch_2d(&tmU, kb * 64, nxt - kHalo);
         }
       }
     }
