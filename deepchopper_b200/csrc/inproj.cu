@@ -34,7 +34,7 @@ constexpr int kN = 144;                       // tokens per MMA: 16 halo + 128
 constexpr int kHalo = 16;
 constexpr uint32_t kUBox = kN * 128;          // 18 KB: 144 token rows x 64 k
 constexpr uint32_t kWBox = 128 * 128;         // 16 KB: 128 channel rows x 64 k
-constexpr int kWStages = 4;
+constexpr int kWStages = 6;   // the ring must cover ~1.5 k cycles of L2 latency at ~270 cycles per stage
 constexpr int kCluster = 2;                   // CTAs that share every weight box through a multicast TMA load
 constexpr uint32_t kWSlice = kWBox / kCluster;  // the rows of a box that one CTA fetches for the whole cluster
 constexpr uint32_t kOutBox = 128 * 128;       // 16 KB: 128 channel rows x 64 tokens (bf16)
@@ -76,8 +76,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t u_base = smem_u32(smem);                       // 4 x 18 KB (each 1024-aligned: 18 KB = 18 x 1024)
   const uint32_t w_base = u_base + 4 * kUBox;
-  const uint32_t o_base = w_base + kWStages * kWBox;            // 4 output boxes: VV h0, VV h1, G h0, G h1
-  float* cst = reinterpret_cast<float*>(smem + 4 * kUBox + kWStages * kWBox + 4 * kOutBox);  // [768][5]: b_in, w0, w1, w2, cb
+  const uint32_t o_base = w_base + kWStages * kWBox;            // 2 output boxes (one per token half; VV then G)
+  float* cst = reinterpret_cast<float*>(smem + 4 * kUBox + kWStages * kWBox + 2 * kOutBox);  // [768][5]: b_in, w0, w1, w2, cb
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 768 * 5);
   const uint32_t bar_base = smem_u32(bars);
   enum { U_FULL = 0, U_EMPTY = 4, W_FULL = 8, W_EMPTY = W_FULL + kWStages, R_FULL = W_EMPTY + kWStages, R_EMPTY = R_FULL + 3,
@@ -254,7 +254,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           const uint32_t t_v = tmem_base + lane_off + 1 * kRegionStride + kHalo + 64 * half;
           const uint32_t obox = o_base + half * kOutBox + row * 128;
           // wait until the previous unit's store from this box has finished reading it
-          if (storer) bulk_wait_read<1>();
+          if (storer) bulk_wait_read<0>();
           bar_sync(2 + half, 128);
           tr(420);
 #pragma unroll
@@ -306,7 +306,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           tr(450);
           tc_fence_after();
           const uint32_t t_x0 = tmem_base + lane_off + 2 * kRegionStride + kHalo + 64 * half;
-          const uint32_t obox = o_base + (2 + half) * kOutBox + row * 128;
+          const uint32_t obox = o_base + half * kOutBox + row * 128;
           // The accumulator goes to registers and the region back to the MMA warp BEFORE the wait for the staging box
           // (the previous unit's TMA store takes ~1.7 k cycles to read it): x0 of the next unit was stalling on that.
           uint32_t ra[32], rb[32], ha0, ha1;
@@ -318,7 +318,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(R_EMPTY + 2));
           tr(460);
-          if (storer) bulk_wait_read<1>();
+          if (storer) bulk_wait_read<0>();
           bar_sync(2 + half, 128);
           tr(470);
           if (row_start && half == 0) ha0 = ha1 = __float_as_uint(-b0);
@@ -339,7 +339,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
           fence_proxy_async();
           bar_sync(2 + half, 128);
           if (storer) {
-            tma_store_3d(&tmGate, o_base + (2 + half) * kOutBox, l0 + 64 * half, g * 128, b);
+            tma_store_3d(&tmGate, o_base + half * kOutBox, l0 + 64 * half, g * 128, b);
             bulk_commit();
           }
           tr(480);
@@ -360,7 +360,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
 int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorMap& tm_w, const CUtensorMap& tm_vv,
                        const CUtensorMap& tm_gate, const InprojParams& p) {
-  const size_t smem = 4 * kUBox + kWStages * kWBox + 4 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
+  const size_t smem = 4 * kUBox + kWStages * kWBox + 2 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
   auto kern = p.trace ? &inproj_conv_kernel<true> : &inproj_conv_kernel<false>;
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(kern), smem));
   int clusters = ctx->sm_count / kCluster;
