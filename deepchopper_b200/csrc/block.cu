@@ -309,22 +309,11 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       }
     }
   } else if (warp == 3) {
-    // ===== y-tile loader (one tile ahead) + L2 prefetch of the y tile and the residual rows TWO tiles ahead =====
-    // All clusters run in lockstep, so what a tile reads (192 KB per CTA, 28 MB per round of tiles) would otherwise be
-    // requested from HBM by every SM at the same moment, right when the weight ring needs its last boxes of the tile
-    // (the ring's L2-resident boxes then queued ~5 k cycles behind those loads).  The prefetches carry no completion
-    // and spread the HBM reads over the chunk loop; the loads themselves become L2 hits.
+    // ===== y-tile loader (one tile ahead) + L2 prefetch of the tile's residual rows =====
+    // (Prefetching y and the residual a whole tile earlier was tried: ~142 MB flow through L2 per round of tiles, so
+    // 60 % of the prefetched lines were evicted before use and DRAM reads grew by half for no gain in time.)
     if (lane == 0) {
       const uint32_t afull = lbar(A_FULL);
-      auto prefetch_tile = [&](int pr) {
-        const int tok0 = pr * 256 + (int)rank * 128;
-        const int b = tok0 / p.L, l0 = tok0 % p.L;
-        for (int kc = 0; kc < 4; ++kc) {
-          tma_prefetch_3d(&tmY, l0, kc * 64, b);
-          tma_prefetch_3d(&tmY, l0 + 64, kc * 64, b);
-        }
-        for (int kb = 0; kb < 8; ++kb) tma_prefetch_2d(&tmHin, kb * 32, tok0);
-      };
       auto load_y = [&](int pr) {
         const int tok0 = pr * 256 + (int)rank * 128;
         const int b = tok0 / p.L, l0 = tok0 % p.L;
@@ -333,17 +322,13 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           tma_load_3d_2sm(a_base + kc * kUnitBytes, &tmY, afull, l0, kc * 64, b);
           tma_load_3d_2sm(a_base + kc * kUnitBytes + 8192, &tmY, afull, l0 + 64, kc * 64, b);
         }
+        for (int kb = 0; kb < 8; ++kb) tma_prefetch_2d(&tmHin, kb * 32, tok0);
       };
-      if (pair0 < num_pairs) {
-        for (int kb = 0; kb < 8; ++kb) tma_prefetch_2d(&tmHin, kb * 32, pair0 * 256 + (int)rank * 128);
-        load_y(pair0);
-      }
-      if (pair0 + pair_step < num_pairs) prefetch_tile(pair0 + pair_step);
+      if (pair0 < num_pairs) load_y(pair0);
       uint32_t n = 0;
       for (int pr = pair0; pr + pair_step < num_pairs; pr += pair_step, ++n) {
         mbar_wait(bar(A_EMPTY), n & 1);  // the last fc1 group of tile n has retired: the buffer is free for tile n+1
         load_y(pr + pair_step);
-        if (pr + 2 * pair_step < num_pairs) prefetch_tile(pr + 2 * pair_step);
       }
     }
   }
