@@ -326,7 +326,7 @@ def run_ours(args, rank, local, world):
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01c_traffic.json")
     if dom and os.path.exists(tpath):
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture, scaled
         # from the profiled batch to this run's average launch (bytes per token x tokens per launch)
