@@ -221,3 +221,17 @@ def test_forward_nontrivial_layernorm_affine():
         close(f"logits (random LayerNorm affine) L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
         decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
         assert torch.equal((got[..., 1] > got[..., 0])[decided], (want[..., 1] > want[..., 0])[decided])
+
+
+@pytest.mark.parametrize("B,L", [(1, 128), (1, 256), (3, 128), (7, 384)])
+def test_forward_tiny_batches(ref, gpu, B, L):
+    """Fewer / odd numbers of 128-token tiles than the CTA clusters and pairs of the kernels expect: in_proj's cluster of
+    two repeats the last tile, the block kernel's last CTA pair has an empty second half."""
+    rng = np.random.default_rng(31 + B + L)
+    ids, q = make_batch(rng, B, L)
+    with torch.no_grad():
+        want = ref(ids, q)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    close(f"logits B={B} L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
+    assert torch.equal((got[..., 1] > got[..., 0])[decided], (want[..., 1] > want[..., 0])[decided])
