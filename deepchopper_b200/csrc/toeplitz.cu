@@ -62,7 +62,9 @@ struct ToepParams {
   int L;                   // padded length (multiple of 128, <= cap)
   int cap;                 // table built for reads up to cap tokens
   int n_rt;                // ceil(B / 128)
-  int n_items;             // 256 * n_rt
+  int n_parts;             // output-tile ranges per (channel, row tile): equal MMA work each (see launch_toeplitz_conv)
+  int jb[9];               // part k covers the 256-token output tiles [jb[k], jb[k+1])
+  int n_items;             // 256 * n_rt * n_parts
 };
 
 __device__ __forceinline__ uint32_t tz_pack(float a, float b) {
@@ -130,9 +132,10 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       uint32_t phase = 0;
       const int kP = p.cap / 8 + kTzZeroChunks;  // chunks per channel in the table
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
-        const int c = o / p.n_rt, rt = o % p.n_rt;
+        const int part = o % p.n_parts, cr = o / p.n_parts;
+        const int c = cr / p.n_rt, rt = cr % p.n_rt;
         const __nv_bfloat16* e_ch = p.E + (size_t)c * kP * 64;
-        for (int J = 0; J < n_tiles; ++J) {
+        for (int J = p.jb[part]; J < p.jb[part + 1]; ++J) {
           const int t_hi = min(256 * J + 255, L - 1);
           const int nkc = 2 * (t_hi / 128 + 1);  // 64-token chunks of the input blocks 0..t_hi/128
           const int q0 = (t_hi - 7) / 8;
@@ -159,7 +162,8 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
-        for (int J = 0; J < n_tiles; ++J) {
+        const int part = o % p.n_parts;
+        for (int J = p.jb[part]; J < p.jb[part + 1]; ++J) {
           const int t_hi = min(256 * J + 255, L - 1);
           const int ntile = t_hi - 256 * J + 1;  // 256 or 128
           const int ilast = t_hi / 128;
@@ -198,8 +202,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       int slot = 0;
       uint32_t gphase = 0;
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
-        const int c = o / p.n_rt, rt = o % p.n_rt;
-        for (int t0 = 0; t0 < L; t0 += 64) {
+        const int part = o % p.n_parts, cr = o / p.n_parts;
+        const int c = cr / p.n_rt, rt = cr % p.n_rt;
+        for (int t0 = 256 * p.jb[part]; t0 < min(L, 256 * p.jb[part + 1]); t0 += 64) {
           mbar_wait(gempty(slot), gphase ^ 1);
           mbar_arrive_expect_tx(gfull(slot), kTzBox);
           tma_load_3d(g_base + slot * kTzBox, &tmG, gfull(slot), t0, c, rt * 128);
@@ -220,8 +225,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     uint32_t gphase = 0, acc_phase = 0;
     uint32_t v[32];
     for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
-      const int c = o / p.n_rt, rt = o % p.n_rt;
-      for (int J = 0; J < n_tiles; ++J) {
+      const int part = o % p.n_parts, cr = o / p.n_parts;
+      const int c = cr / p.n_rt, rt = cr % p.n_rt;
+      for (int J = p.jb[part]; J < p.jb[part + 1]; ++J) {
         const int t_hi = min(256 * J + 255, L - 1);
         const int ntile = t_hi - 256 * J + 1;
         mbar_wait(tfull(acc), acc_phase);
@@ -305,7 +311,33 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, int cap, const
   p.L = L;
   p.cap = cap;
   p.n_rt = (B + 127) / 128;
-  p.n_items = 256 * p.n_rt;
+  // Work items are (channel, 128-row tile, range of output tiles).  A long read's batch has few row tiles (one for
+  // 16-32 kb reads): 256 items over 148 SMs are 1.73 waves, i.e. 14 % of the machine idle in the second one.  The output
+  // tiles of an item are therefore dealt to up to 8 parts of equal MMA work (tile J costs ~4 J + 4 chunks), enough
+  // parts for >= 8 waves.
+  const int n_tiles = (L + 255) / 256;
+  int parts = 1;
+  const int base_items = 256 * p.n_rt;
+  // (only where the kernel is MMA-bound, L >= 4096: a part re-reads the input blocks of the parts before it, which
+  // costs the HBM-bound short reads 30 %)
+  if (L >= 4096 && base_items < 8 * ctx->sm_count) parts = (8 * ctx->sm_count + base_items - 1) / base_items;
+  if (parts > 8) parts = 8;
+  if (parts > n_tiles) parts = n_tiles;
+  p.n_parts = parts;
+  {
+    const double total = 2.0 * n_tiles * n_tiles + 2.0 * n_tiles;
+    int J = 0;
+    p.jb[0] = 0;
+    for (int k = 1; k < parts; ++k) {
+      while (J < n_tiles && 2.0 * J * J + 2.0 * J < total * k / parts) ++J;
+      if (J <= p.jb[k - 1]) J = p.jb[k - 1] + 1;  // every part gets at least one tile
+      if (J > n_tiles - (parts - k)) J = n_tiles - (parts - k);
+      p.jb[k] = J;
+    }
+    p.jb[parts] = n_tiles;
+    for (int k = parts + 1; k < 9; ++k) p.jb[k] = n_tiles;
+  }
+  p.n_items = base_items * parts;
   const size_t want = (size_t)kTzAStages * kTzStage + (size_t)kTzGSlots * kTzBox + 1024 + 512;
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&toeplitz_kernel), want));
   const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
