@@ -318,9 +318,9 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, int cap, const
   const int n_tiles = (L + 255) / 256;
   int parts = 1;
   const int base_items = 256 * p.n_rt;
-  // (only where the kernel is MMA-bound, L >= 4096: a part re-reads the input blocks of the parts before it, which
+  // (only where the kernel is MMA-bound, L >= 2048: a part re-reads the input blocks of the parts before it, which
   // costs the HBM-bound short reads 30 %)
-  if (L >= 4096 && base_items < 8 * ctx->sm_count) parts = (8 * ctx->sm_count + base_items - 1) / base_items;
+  if (L >= 2048 && base_items < 8 * ctx->sm_count) parts = (8 * ctx->sm_count + base_items - 1) / base_items;
   if (parts > 8) parts = 8;
   if (parts > n_tiles) parts = n_tiles;
   p.n_parts = parts;
