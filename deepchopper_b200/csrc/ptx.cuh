@@ -86,6 +86,39 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Elected-lane forms for warp-converged producers (whole warp runs the loop; see umma_bf16_x4_e): a producer inside an
+// `if (lane == 0)` branch pays an R2UR / ELECT waterfall per TMA instruction (~800 cycles per stage in the Toeplitz kernel).
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint32_t bar, uint32_t bytes, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "setp.ne.b32 pe, %2, 0;\n"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "r"(bytes), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_e(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "setp.ne.b32 pe, %6, 0;\n"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      "}\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_e(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "setp.ne.b32 pe, %4, 0;\n"
+      "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+      "}\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "r"(elected)
+      : "memory");
+}
 // TMA store shared -> global (bulk-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

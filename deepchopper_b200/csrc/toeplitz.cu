@@ -26,6 +26,9 @@
 #include "ptx.cuh"
 #include "toeplitz.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace dcb {
 
 using namespace ptx;
@@ -65,6 +68,7 @@ struct ToepParams {
   int n_parts;             // output-tile ranges per (channel, row tile): equal MMA work each (see launch_toeplitz_conv)
   int jb[9];               // part k covers the 256-token output tiles [jb[k], jb[k+1])
   int n_items;             // 256 * n_rt * n_parts
+  long long* trace;        // optional timeline trace (DCB200_TRACE=toeplitz), or null
 };
 
 __device__ __forceinline__ uint32_t tz_pack(float a, float b) {
@@ -72,6 +76,7 @@ __device__ __forceinline__ uint32_t tz_pack(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <bool kTrace>
 __global__ void __launch_bounds__(kTzThreads, 1)
 toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG,
                 const __grid_constant__ CUtensorMap tmY, const ToepParams p) {
@@ -126,10 +131,12 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
   const int n_tiles = (L + 255) / 256;
 
   if (warp == 0) {
-    // ===== producer: A tile + E window per stage =====
-    if (lane == 0) {
+    // ===== producer: A tile + E window per stage (whole warp runs the loop, the elected lane issues) =====
+    {
+      const uint32_t el = elect_one() ? 1u : 0u;
       int stage = 0;
       uint32_t phase = 0;
+      TracerT<kTrace> tr{(kTrace && p.trace && blockIdx.x == 0 && el) ? p.trace + 2 * 2 * kTraceCap : nullptr, 0};
       const int kP = p.cap / 8 + kTzZeroChunks;  // chunks per channel in the table
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
         const int part = o % p.n_parts, cr = o / p.n_parts;
@@ -140,13 +147,15 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
           const int nkc = 2 * (t_hi / 128 + 1);  // 64-token chunks of the input blocks 0..t_hi/128
           const int q0 = (t_hi - 7) / 8;
           for (int kc = 0; kc < nkc; ++kc) {
+            tr(300);
             mbar_wait(aempty(stage), phase ^ 1);
-            mbar_arrive_expect_tx(afull(stage), kTzBox + kTzWin);
+            tr(310);
+            mbar_arrive_expect_tx_e(afull(stage), kTzBox + kTzWin, el);
             const uint32_t dst = a_base + stage * kTzStage;
-            tma_load_3d(dst, &tmV, afull(stage), kc * 64, c, rt * 128);
+            tma_load_3d_e(dst, &tmV, afull(stage), kc * 64, c, rt * 128, el);
             // window: core matrices i = q, q-1, ..., q-39 (table position p = cap/8 - 1 - i)
             const int q = q0 - 8 * kc;
-            bulk_load_1d(dst + kTzBox, e_ch + (size_t)(p.cap / 8 - 1 - q) * 64, kTzWin, afull(stage));
+            bulk_load_1d_e(dst + kTzBox, e_ch + (size_t)(p.cap / 8 - 1 - q) * 64, kTzWin, afull(stage), el);
             if (++stage == kTzAStages) {
               stage = 0;
               phase ^= 1;
@@ -159,6 +168,7 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     // ===== MMA issuer: the whole warp runs the loop, the elected lane issues (ptx.cuh umma_bf16_x4_e) =====
     {
       const uint32_t el = elect_one() ? 1u : 0u;
+      TracerT<kTrace> tr{(kTrace && p.trace && blockIdx.x == 0 && el) ? p.trace : nullptr, 0};
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
@@ -167,7 +177,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
           const int t_hi = min(256 * J + 255, L - 1);
           const int ntile = t_hi - 256 * J + 1;  // 256 or 128
           const int ilast = t_hi / 128;
+          tr(90);
           mbar_wait(tempty(acc), acc_phase ^ 1);
+          tr(100);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 256;
           const uint32_t idesc_full = make_idesc_bf16(128, ntile, false, false);
@@ -175,7 +187,9 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
           for (int i = 0; i <= ilast; ++i) {
             const uint32_t idesc = (i == ilast) ? idesc_diag : idesc_full;
             for (int hh = 0; hh < 2; ++hh) {
+              tr(110);
               mbar_wait(afull(stage), phase);
+              tr(120);
               tc_fence_after();
               const uint32_t a_addr = a_base + stage * kTzStage;
               // A: +32 B per K = 16 slice inside the swizzled tile; B: the window slides by two core matrices (256 B)
@@ -224,13 +238,16 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     int slot = 0, acc = 0, prev_slot = -1;
     uint32_t gphase = 0, acc_phase = 0;
     uint32_t v[32];
+    TracerT<kTrace> tr{(kTrace && p.trace && blockIdx.x == 0 && warp == 4 && lane == 0) ? p.trace + 2 * kTraceCap : nullptr, 0};
     for (int o = blockIdx.x; o < p.n_items; o += gridDim.x) {
       const int part = o % p.n_parts, cr = o / p.n_parts;
       const int c = cr / p.n_rt, rt = cr % p.n_rt;
       for (int J = p.jb[part]; J < p.jb[part + 1]; ++J) {
         const int t_hi = min(256 * J + 255, L - 1);
         const int ntile = t_hi - 256 * J + 1;
+        tr(400);
         mbar_wait(tfull(acc), acc_phase);
+        tr(410);
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
         for (int x = 0; x < ntile / 64; ++x) {
@@ -273,6 +290,7 @@ toeplitz_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
         }
         tc_fence_before();
         mbar_arrive(tempty(acc));
+        tr(480);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -339,10 +357,23 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, int cap, const
   }
   p.n_items = base_items * parts;
   const size_t want = (size_t)kTzAStages * kTzStage + (size_t)kTzGSlots * kTzBox + 1024 + 512;
-  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&toeplitz_kernel), want));
+  p.trace = nullptr;
+  {
+    const char* te = getenv("DCB200_TRACE");
+    static thread_local bool traced_once = false;
+    if (te && !strcmp(te, "toeplitz") && !traced_once) {
+      traced_once = true;
+      DevBuf& bt = ctx->buf("trace");
+      DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
+      DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
+      p.trace = bt.as<long long>();
+    }
+  }
+  auto kern = p.trace ? &toeplitz_kernel<true> : &toeplitz_kernel<false>;
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(kern), want));
   const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
   ProfScope prof(ctx, K_TOEP);
-  toeplitz_kernel<<<grid, kTzThreads, want, ctx->stream>>>(tm_vv, tm_gate, tm_y, p);
+  kern<<<grid, kTzThreads, want, ctx->stream>>>(tm_vv, tm_gate, tm_y, p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }
