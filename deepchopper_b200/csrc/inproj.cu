@@ -34,7 +34,7 @@ constexpr int kN = 144;                       // tokens per MMA: 16 halo + 128
 constexpr int kHalo = 16;
 constexpr uint32_t kUBox = kN * 128;          // 18 KB: 144 token rows x 64 k
 constexpr uint32_t kWBox = 128 * 128;         // 16 KB: 128 channel rows x 64 k
-constexpr int kWStages = 6;   // the ring must cover ~1.5 k cycles of L2 latency at ~270 cycles per stage
+constexpr int kWStages = 7;   // the ring must cover ~1.5 k cycles of L2 latency at ~270 cycles per stage
 constexpr int kCluster = 2;                   // CTAs that share every weight box through a multicast TMA load
 constexpr uint32_t kWSlice = kWBox / kCluster;  // the rows of a box that one CTA fetches for the whole cluster
 constexpr uint32_t kOutBox = 128 * 128;       // 16 KB: 128 channel rows x 64 tokens (bf16)
@@ -77,8 +77,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   const uint32_t u_base = smem_u32(smem);                       // 4 x 18 KB (each 1024-aligned: 18 KB = 18 x 1024)
   const uint32_t w_base = u_base + 4 * kUBox;
   const uint32_t o_base = w_base + kWStages * kWBox;            // 2 output boxes (one per token half; VV then G)
-  float* cst = reinterpret_cast<float*>(smem + 4 * kUBox + kWStages * kWBox + 2 * kOutBox);  // [768][5]: b_in, w0, w1, w2, cb
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cst + 768 * 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kUBox + kWStages * kWBox + 2 * kOutBox);
   const uint32_t bar_base = smem_u32(bars);
   enum { U_FULL = 0, U_EMPTY = 4, W_FULL = 8, W_EMPTY = W_FULL + kWStages, R_FULL = W_EMPTY + kWStages, R_EMPTY = R_FULL + 3,
          N_BARS = R_EMPTY + 3 };
@@ -112,14 +111,6 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
   if (warp == 2) {
     tmem_alloc(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish();
-  }
-  // per-channel constants: z = acc + b_in ; zc[t] = w0 z[t-2] + w1 z[t-1] + w2 z[t] + cb
-  for (int i = threadIdx.x; i < 768; i += kThreads) {
-    cst[i * 5 + 0] = p.b_in[i];
-    cst[i * 5 + 1] = p.short_w[i * 3 + 0];
-    cst[i * 5 + 2] = p.short_w[i * 3 + 1];
-    cst[i * 5 + 3] = p.short_w[i * 3 + 2];
-    cst[i * 5 + 4] = p.short_b[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -241,10 +232,13 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         const int ch = g * 128 + row;  // my channel within each third
         // ---- VV: sc(x1) * sc(v) ----------------------------------------------------------------------------------
         {
-          const float* c1 = cst + (256 + ch) * 5;
-          const float* cv = cst + (512 + ch) * 5;
-          const float b1 = c1[0], w10 = c1[1], w11 = c1[2], w12 = c1[3], cb1 = fmaf(c1[0], (c1[1] + c1[2]) + c1[3], c1[4]);
-          const float bv = cv[0], wv0 = cv[1], wv1 = cv[2], wv2 = cv[3], cbv = fmaf(cv[0], (cv[1] + cv[2]) + cv[3], cv[4]);
+          // per-channel constants straight from global memory (15 scalars per thread and unit, requested before the wait
+          // for the accumulators so their latency is hidden; a shared-memory table cost a weight-ring stage)
+          const int i1 = 256 + ch, iv = 512 + ch;
+          const float b1 = __ldg(p.b_in + i1), w10 = __ldg(p.short_w + 3 * i1), w11 = __ldg(p.short_w + 3 * i1 + 1),
+                      w12 = __ldg(p.short_w + 3 * i1 + 2), cb1 = fmaf(b1, (w10 + w11) + w12, __ldg(p.short_b + i1));
+          const float bv = __ldg(p.b_in + iv), wv0 = __ldg(p.short_w + 3 * iv), wv1 = __ldg(p.short_w + 3 * iv + 1),
+                      wv2 = __ldg(p.short_w + 3 * iv + 2), cbv = fmaf(bv, (wv0 + wv1) + wv2, __ldg(p.short_b + iv));
           tr(400);
           mbar_wait(bar(R_FULL + 0), use & 1);
           mbar_wait(bar(R_FULL + 1), use & 1);
@@ -299,8 +293,8 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
         }
         // ---- G: sc(x0) ---------------------------------------------------------------------------------------------
         {
-          const float* c0 = cst + ch * 5;
-          const float b0 = c0[0], w0 = c0[1], w1 = c0[2], w2 = c0[3], cb0 = fmaf(c0[0], (c0[1] + c0[2]) + c0[3], c0[4]);
+          const float b0 = __ldg(p.b_in + ch), w0 = __ldg(p.short_w + 3 * ch), w1 = __ldg(p.short_w + 3 * ch + 1),
+                      w2 = __ldg(p.short_w + 3 * ch + 2), cb0 = fmaf(b0, (w0 + w1) + w2, __ldg(p.short_b + ch));
           tr(440);
           mbar_wait(bar(R_FULL + 2), use & 1);
           tr(450);
@@ -360,7 +354,7 @@ inproj_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
 
 int launch_inproj_conv(dcb200_ctx* ctx, const CUtensorMap& tm_u, const CUtensorMap& tm_w, const CUtensorMap& tm_vv,
                        const CUtensorMap& tm_gate, const InprojParams& p) {
-  const size_t smem = 4 * kUBox + kWStages * kWBox + 2 * kOutBox + 768 * 5 * 4 + 32 * 8 + 1024;
+  const size_t smem = 4 * kUBox + kWStages * kWBox + 2 * kOutBox + 40 * 8 + 1024;
   auto kern = p.trace ? &inproj_conv_kernel<true> : &inproj_conv_kernel<false>;
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(kern), smem));
   int clusters = ctx->sm_count / kCluster;
