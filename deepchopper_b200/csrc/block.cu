@@ -293,21 +293,6 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 2) {
-    // ===== second residual boxes: columns [64 part + 32, +32) of h0 land in K box `part` of the A buffer as soon as the
-    // out_proj MMAs have retired (the y tile is dead from then until m is written over it), i.e. while the epilogue
-    // warps are still busy with the previous tile's stores: epilogue O finds them resident.
-    if (lane == 0) {
-      uint32_t n = 0;
-      for (int pr = pair0; pr < num_pairs; pr += pair_step, ++n) {
-        const int tok0 = pr * 256 + (int)rank * 128;
-        mbar_wait(bar(Y_DEAD), n & 1);
-        for (int q = 0; q < 4; ++q) {
-          mbar_arrive_expect_tx(bar(R2_FULL + q), kUnitBytes);
-          tma_load_2d(a_base + q * kUnitBytes, &tmHin, bar(R2_FULL + q), q * 64 + 32, tok0);
-        }
-      }
-    }
   } else if (warp == 3) {
     // ===== y-tile loader (one tile ahead) + L2 prefetch of the tile's residual rows =====
     // (Prefetching y and the residual a whole tile earlier was tried: ~142 MB flow through L2 per round of tiles, so
@@ -373,6 +358,10 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         ++e1;
         tr(381);
         tc_fence_after();
+        if (n == 0 && storer) {  // first tile: the out_proj MMAs have retired, the y buffer is free for my second box
+          mbar_arrive_expect_tx(bar(R2_FULL + part), kUnitBytes);
+          tma_load_2d(a_base + part * kUnitBytes, &tmHin, bar(R2_FULL + part), colA + 32, tok0);
+        }
         tmem_ld32(tmem_base + lane_off + 256 + colA, v);
         tmem_ld32(tmem_base + lane_off + 256 + colA + 32, w2);
         tmem_ld_wait();
@@ -381,8 +370,8 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         if (lane == 0) mbar_arrive_remote(t1_empty);  // acc1 drained
         tr(382);
         uint64_t sum2 = f2_pack(0.f, 0.f), sq2 = sum2;  // (even, odd) column partial sums: packed fp32x2 arithmetic
-        // The box in the A buffer (my columns 32-63) has been resident for a while; the one in my staging slot (columns
-        // 0-31) was requested at the very end of the previous tile, so it goes second.
+        // Both boxes were requested by my part's storer thread at the end of the previous tile's final epilogue: the one
+        // in the A buffer (my columns 32-63) first, the one in my staging slot (columns 0-31) second.
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
           uint32_t (&x)[32] = st ? v : w2;
@@ -575,23 +564,33 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       // Three boxes (h_out columns [64p, +32), [64p+32, +32) as fp32, u columns [64p, +64) as bf16; 16 KB each) go
       // through my part's slot to TMA stores: the LSU store path sustains only ~24 B/clk per SM here (its queue of
       // outstanding L2 writes is latency bound), TMA is not.  The slot is rewritten once the previous store has read it.
-      const uint32_t own = my_slot + row * 128;  // my row of the 128-row box, 16-byte chunks XOR-swizzled by (row & 7)
+      // Three boxes per column part (h_out columns [64p, +32), [64p+32, +32) as fp32, u columns [64p, +64) as bf16; 16 KB
+      // each) leave through TMA stores.  Two staging slots per part: my slot in G and K box p of the A buffer (dead once
+      // the next tile's out_proj MMAs have retired).  With a single slot every box waited ~2.5 k cycles for the previous
+      // store to finish reading it; now the third box reuses the first slot only after two stagings.
+      const bool has_next = pr + pair_step < num_pairs;
+      const uint32_t own = my_slot + row * 128;  // my row of a 128-row box, 16-byte chunks XOR-swizzled by (row & 7)
+      const uint32_t y_slot = a_base + part * kUnitBytes;
+      const uint32_t own_y = y_slot + row * 128;
 #pragma unroll
-      for (int st = 0; st < 2; ++st) {
-        const uint32_t (&x)[32] = st ? v2 : v;
-        if (st == 1) bar_sync(2 + part, 128);  // (the storer arrives after the first store has read the slot)
+      for (int q = 0; q < 8; ++q) sts128(own + (((uint32_t)q ^ sw) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      fence_proxy_async();
+      bar_sync(2 + part, 128);
+      if (storer) {
+        tma_store_2d(&tmHout, my_slot, colA, tok0);
+        bulk_commit();
+      }
+      bar_sync(6 + quad, 128);  // pair sums of all four parts are in place
+      // the A buffer: free once out_proj of the NEXT tile has read the y tile that was loaded into it (after the last
+      // tile of this CTA pair nothing is loaded, m is dead since the last fc1 group retired)
+      if (has_next) mbar_wait(bar(Y_DEAD), (n + 1) & 1);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sts128(own + (((uint32_t)q ^ sw) << 4), x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-        fence_proxy_async();
-        bar_sync(2 + part, 128);
-        if (storer) {
-          tma_store_2d(&tmHout, my_slot, colA + st * 32, tok0);
-          bulk_commit();
-        }
-        if (st == 0) {
-          bar_sync(6 + quad, 128);  // pair sums of all four parts are in place
-        }
-        if (storer) bulk_wait_read<0>();
+      for (int q = 0; q < 8; ++q) sts128(own_y + (((uint32_t)q ^ sw) << 4), v2[4 * q], v2[4 * q + 1], v2[4 * q + 2], v2[4 * q + 3]);
+      fence_proxy_async();
+      bar_sync(2 + part, 128);
+      if (storer) {
+        tma_store_2d(&tmHout, y_slot, colA + 32, tok0);
+        bulk_commit();
       }
       tr(551);
       float2 sa = stats[row];
@@ -603,7 +602,7 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       const float mean = sa.x * (1.0f / 256.0f);
       const float rstd = rsqrtf(fmaxf(sa.y * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
       const uint64_t rs2 = f2_pack(rstd, rstd), nm2 = f2_pack(-mean * rstd, -mean * rstd);
-      {  // u: my 64 bf16 columns (128 B per row), normalised in registers while the second h_out store drains
+      {  // u: my 64 bf16 columns (128 B per row), normalised in registers while the h_out stores drain
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t (&x)[32] = c ? v2 : v;
@@ -617,7 +616,8 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
             }
           }
         }
-        bar_sync(2 + part, 128);  // slot free again
+        if (storer) bulk_wait_read<1>();  // the first store (my slot) has been read; the second may still be reading
+        bar_sync(2 + part, 128);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const uint32_t (&x)[32] = c ? v2 : v;
@@ -630,10 +630,16 @@ block_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         if (storer) {
           tma_store_2d(&tmU, my_slot, colA, tok0);
           bulk_commit();
-          bulk_wait_read<0>();
-          if (pr + pair_step < num_pairs) {  // next tile's first residual box
+          if (has_next) {  // next tile's residual boxes: into each slot as soon as its store has been read
+            const int ntok0 = (pr + pair_step) * 256 + (int)rank * 128;
+            bulk_wait_read<1>();
+            mbar_arrive_expect_tx(bar(R2_FULL + part), kUnitBytes);
+            tma_load_2d(y_slot, &tmHin, bar(R2_FULL + part), colA + 32, ntok0);
+            bulk_wait_read<0>();
             mbar_arrive_expect_tx(my_rfull, kUnitBytes);
-            tma_load_2d(my_slot, &tmHin, my_rfull, colA, (pr + pair_step) * 256 + (int)rank * 128);
+            tma_load_2d(my_slot, &tmHin, my_rfull, colA, ntok0);
+          } else {
+            bulk_wait_read<0>();
           }
         }
       }
