@@ -15,6 +15,7 @@ EXPORTS = [
     "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
     "dcb200_kernel_kind_name", "dcb200_chop_write_bgzf",
+    "dcb200_read_file_inflate", "dcb200_free",
 ]
 
 
@@ -77,6 +78,9 @@ def lib():
     l.dcb200_kernel_kind_name.argtypes = [i32]
     l.dcb200_kernel_kind_name.restype = C.c_char_p
     pp = C.POINTER(ChopParams)
+    l.dcb200_read_file_inflate.argtypes = [C.c_char_p, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32)]
+    l.dcb200_free.argtypes = [vp]
+    l.dcb200_free.restype = None
     l.dcb200_chop_write_bgzf.argtypes = [C.POINTER(FastqIndexC), i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, C.c_char_p,
                                          i32, i32, vp, vp]
     l.dcb200_smooth_chop.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]

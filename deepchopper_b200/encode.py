@@ -79,17 +79,19 @@ class FastqIndex:
         return self.buf[o:o + int(self.qual_len[r])].tobytes()
 
 
-def read_fastq_bytes(path: str) -> np.ndarray:
-    """Plain / gzip / bgzip FASTQ -> uint8 array (compression sniffed like src/output/writefq.rs:84-135)."""
-    with open(path, "rb") as f:
-        magic = f.read(2)
-    if magic == b"\x1f\x8b":
-        with gzip.open(path, "rb") as f:
-            data = f.read()
-    else:
-        with open(path, "rb") as f:
-            data = f.read()
-    return np.frombuffer(data, dtype=np.uint8)
+def read_fastq_bytes(path: str, threads: int = 0) -> np.ndarray:
+    """Plain / gzip / bgzip FASTQ -> uint8 array (compression sniffed like src/output/writefq.rs:84-135).  Native:
+    dcb200_read_file_inflate inflates BGZF blocks on host threads (a plain gzip stream is inherently one thread)."""
+    import ctypes as C
+    import os
+    ptr, n, kind = C.c_void_p(), C.c_int64(0), C.c_int32(0)
+    check(lib().dcb200_read_file_inflate(os.fsencode(path), int(threads), C.byref(ptr), C.byref(n), C.byref(kind)))
+    try:
+        if n.value == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+    finally:
+        lib().dcb200_free(ptr)
 
 
 def index_fastq(buf: np.ndarray) -> FastqIndex:

@@ -22,6 +22,7 @@
  *                           src/output/split.rs:60-136,171-226,260-320 and the gating of src/bin/predict.rs:137-187
  *   dcb200_smooth_chop_logits  the same after src/smooth/predict.rs:263-317 (argmax(2) + drop target == -100)
  *   dcb200_chop_write_bgzf  src/bin/predict.rs:266-364 (write loop), src/output/split.rs:60-226, src/output/writefq.rs
+ *   dcb200_read_file_inflate  src/output/writefq.rs:84-193 (plain / gzip / bgzip readers), deepchopper/data/only_fq.py:21-85
  *   dcb200_predict_batch_host  the whole per-batch hot loop of `deepchopper predict` + the interval step of
  *                           `deepchopper chop` (cli.py:66-152, src/bin/predict.rs:130-192) on host buffers
  */
@@ -184,6 +185,15 @@ int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, const uint8_
                            const int32_t* n_adapter, const int32_t* adapter_iv, int32_t adapter_stride,
                            const int32_t* n_keep, const int32_t* keep_iv, int32_t keep_stride, const char* path,
                            int32_t threads, int32_t level, int64_t* n_records, int64_t* n_text_bytes);
+
+/* ---- FASTQ ingest, file level: plain / gzip / BGZF file -> one host buffer ----------------------------
+ * Replaces the compression sniffing and single-threaded readers of src/output/writefq.rs:84-193 and the file access
+ * of deepchopper/data/only_fq.py:21-85 (pyfastx).  BGZF blocks (bgzip, and what dcb200_chop_write_bgzf writes) are
+ * inflated on `threads` host threads (<= 0: all cores) with their CRCs checked; a plain gzip stream by one thread; any
+ * other file is returned as is.  *out is malloc'ed and released with dcb200_free; *kind (may be NULL) = 0 plain,
+ * 1 gzip, 2 BGZF. */
+int dcb200_read_file_inflate(const char* path, int32_t threads, uint8_t** out, int64_t* out_len, int32_t* kind);
+void dcb200_free(void* p);
 
 /* ---- diagnostics (used by the parity tests to localise a mismatch) ---------------------------------
  * dcb200_forward_debug == dcb200_forward that stops after `stop_stage` kernels of the forward chain

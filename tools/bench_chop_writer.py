@@ -89,3 +89,19 @@ python_writer(os.path.join(tmp, "p.fq.gz"), sample)
 dt = time.perf_counter() - t0
 text = float((ix.seq_len[:sample].astype(np.int64) * 2).sum())
 print(f"python/zlib 1 thread ({sample} reads): {dt * 1e3:8.1f} ms  ~{text * 0.93 / dt / 1e6:6.1f} MB/s text  {sample / dt / 1e3:6.1f} k reads/s")
+
+# ---- reading the BGZF file back (dcb200_read_file_inflate) next to Python's gzip module -------------------
+import gzip  # noqa: E402
+
+from deepchopper_b200.encode import read_fastq_bytes  # noqa: E402
+
+path = os.path.join(tmp, "o.fq.gz")
+for t in (1, 2, 0):
+    t0 = time.perf_counter()
+    got = read_fastq_bytes(path, threads=t)
+    dt = time.perf_counter() - t0
+    print(f"native inflate threads={t or os.cpu_count():3d}: {dt * 1e3:8.1f} ms  {got.size / dt / 1e6:8.1f} MB/s text")
+t0 = time.perf_counter()
+ref = gzip.open(path, "rb").read()
+dt = time.perf_counter() - t0
+print(f"python gzip 1 thread       : {dt * 1e3:8.1f} ms  {len(ref) / dt / 1e6:8.1f} MB/s text   identical: {ref == got.tobytes()}")
