@@ -327,3 +327,44 @@ def parse_fastq_text(text: str) -> List[FastqRecord]:
         recs.append(FastqRecord(name, desc, lines[i + 1], lines[i + 3]))
         i += 4
     return recs
+
+
+# ---- StatResult / collect_statistics_for_predicts (src/smooth/stat.rs:16-308) -----------------------------------------
+
+FLANK_SIZE_COUNT_PLOYA = 5   # src/smooth/stat.rs:16
+
+
+def collect_statistics_for_predicts(predicts, smooth_window_size: int, min_interval_size: int,
+                                    approved_interval_number: int, internal_threshold: float, ploya_threshold: int):
+    """src/smooth/stat.rs:222-308, literally: reads shorter than MIN_READ_LEN are skipped; the rayon reduce merges the
+    per-read results in input order.  Returns a plain dict with the fields of StatResult (stat.rs:19-41)."""
+    import numpy as np
+    res = dict(predicts_with_chop=[], smooth_predicts_with_chop=[], smooth_internal_predicts=[], smooth_intervals={},
+               original_intervals={}, total_truncated=0, smooth_only_one=[], smooth_only_one_with_ploya=[],
+               total_predicts=0, smooth_intervals_relative_pos=[])
+    for p in predicts:
+        if len(p.seq) < MIN_READ_LEN:
+            continue
+        res["total_predicts"] += 1
+        if p.is_truncated:
+            res["total_truncated"] += 1
+        regions = p.prediction_region()
+        if regions:
+            res["predicts_with_chop"].append(p.id)
+            res["original_intervals"][p.id] = list(regions)
+        smooth = p.smooth_and_select_intervals(smooth_window_size, min_interval_size, approved_interval_number)
+        if smooth:
+            res["smooth_predicts_with_chop"].append(p.id)
+            res["smooth_intervals"][p.id] = list(smooth)
+            if len(smooth) == 1:
+                res["smooth_only_one"].append(p.id)
+                s0 = smooth[0][0]
+                count = p.seq[max(0, s0 - FLANK_SIZE_COUNT_PLOYA):s0].count("A")
+                if count >= ploya_threshold:
+                    res["smooth_only_one_with_ploya"].append(p.id)
+            for (_, e) in smooth:
+                rel = np.float32(e) / np.float32(len(p.seq))          # `region.1 as f32 / predict.seq_len() as f32`
+                res["smooth_intervals_relative_pos"].append(float(rel))
+                if rel < np.float32(internal_threshold):
+                    res["smooth_internal_predicts"].append(p.id)
+    return res
