@@ -17,7 +17,7 @@ import torch
 from ._native import ChopParams, FastqIndexC, check, lib
 from .encode import FastqIndex, index_fastq, read_fastq_bytes
 from .smooth import CHOP_TYPES, MIN_READ_LEN, _ID_TABLE, smooth_chop_device
-from .writer import IGNORE, list_batches
+from .writer import COMPACT_SUFFIX, IGNORE, list_batches, read_batch_compact
 
 
 @dataclass
@@ -78,7 +78,7 @@ def load_prediction_batches(paths: Iterable[str], max_batches: Optional[int] = N
     batches = []
     for f in files:
         try:
-            d = torch.load(f, map_location="cpu")
+            d = read_batch_compact(f) if f.endswith(COMPACT_SUFFIX) else torch.load(f, map_location="cpu")
         except Exception as e:  # noqa: BLE001  (src/smooth/predict.rs:246-256: report and skip)
             print(f"load pt {f} fail caused by Error: {e!r}")
             continue
@@ -112,7 +112,39 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
     pseq_len = np.zeros(R, np.int32)
     keepalive = []
     n_pred_ids = set()
+    pseq_fastq = None          # predicted sequence of compact batches = the normalised FASTQ sequence (ACGT, else N)
     for d in batches:
+        if d.get("compact"):
+            # compact sidecar: labels only; the sequence the reference decodes from the prediction tensor's tokens is a
+            # function of the FASTQ sequence itself (tokenizer: A C G T -> 7..10, anything else -> N / UNK -> 'N')
+            if pseq_fastq is None:
+                table = np.full(256, ord("N"), dtype=np.uint8)
+                for a, b in zip(b"ACGTacgtUu", b"ACGTACGTTT"):
+                    table[a] = b
+                pseq_fastq = np.ascontiguousarray(table[np.asarray(ix.buf, dtype=np.uint8)])
+                keepalive.append(pseq_fastq)
+            ids = d["ids"]
+            offs = d["offsets"]
+            lens = np.diff(offs).astype(np.int32)
+            qual_lens = np.array([qlen_of.get(i, int(l)) for i, l in zip(ids, lens)], dtype=np.int32)
+            n_ad, ad, n_keep, keep, act = smooth_chop_device(
+                torch.from_numpy(d["labels"]).to(dev), torch.from_numpy(offs[:-1].astype(np.int64)).to(dev),
+                torch.from_numpy(lens).to(dev), params, torch.from_numpy(qual_lens).to(dev), logits=False)
+            n_ad, ad, n_keep, keep, act = (t.cpu().numpy() for t in (n_ad, ad, n_keep, keep, act))
+            n_pred_ids.update(ids)
+            for b, rid in enumerate(ids):
+                r = row_of.get(rid)
+                if r is None:
+                    continue
+                has_pred[r] = 1
+                action[r] = act[b]
+                n_ad_all[r] = n_ad[b]
+                n_keep_all[r] = n_keep[b]
+                ad_all[r, :ad.shape[1]] = ad[b]
+                keep_all[r, :keep.shape[1]] = keep[b]
+                pseq_ptr[r] = pseq_fastq.ctypes.data + int(ix.seq_off[r])
+                pseq_len[r] = lens[b]
+            continue
         pred = d["prediction"].float().contiguous()
         target = d["target"].to(torch.int64).numpy()
         seq = d["seq"].to(torch.int64).numpy()

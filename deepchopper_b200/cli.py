@@ -53,6 +53,11 @@ def _predict_worker(rank: int, world: int, args):
         from .encode import encode_batch_device
         _, so, qo, ln, st = item
         tok, qual = encode_batch_device(pipe.blob, so, qo, ln, b.Lpad, None, b.Lrow)
+        if args.compact:   # labels only, bit-packed: read back by this package's `chop`
+            _, labels = model.forward_tokens(tok, qual, False, True)
+            writer.write_batch_compact(args.output, rank, idx, labels, lens[b.rows], b.Lpad, [ix.name(r) for r in b.rows],
+                                       truncated[b.rows])
+            continue
         logits, _ = model.forward_tokens(tok, qual, True, False)
         d = writer.batch_dict(logits, tok, qual, encode.id_rows(ix, b.rows, truncated[b.rows]), lens[b.rows], b.Lpad)
         writer.write_batch(args.output, rank, idx, d)
@@ -99,6 +104,9 @@ def build_parser():
     pr.add_argument("--seed", type=int, default=0)
     pr.add_argument("--bucket", action="store_true", help="length-bucketed batches instead of FASTQ-order batches")
     pr.add_argument("--token-budget", type=int, default=512 * 1024)
+    pr.add_argument("--compact", action="store_true",
+                    help="write bit-packed label sidecars (1 bit per base) instead of the reference's .pt dicts "
+                         "(28 bytes per token); only this package's `chop` reads them")
     pr.set_defaults(fn=cmd_predict)
     ch = sub.add_parser("chop", help="smooth predictions and cut reads (cli.py:155-198 -> deepchopper-chop)")
     ch.add_argument("predicts", nargs="+")

@@ -78,6 +78,20 @@ def test_chop_output_bit_exact(tmp_path, chop_type, ocq):
     got = gzip.open(out, "rb").read().decode()
     assert (npred, nrec) == (want_pred, want_rec)
     assert got == want
+    # the compact sidecar (labels only, bit-packed) gives the same output as the .pt dicts
+    cdir = tmp_path / "compact"
+    for i, d in enumerate(dicts):
+        lab = (d["prediction"][..., 1] > d["prediction"][..., 0]).to(torch.uint8)
+        keep = (d["target"] != -100)
+        lens_b = keep.sum(dim=1).numpy()
+        ids = [bytes(d["id"][b, 2:2 + int(d["id"][b, 0])].to(torch.uint8).numpy()).decode("latin1") for b in range(lab.shape[0])]
+        writer.write_batch_compact(str(cdir), 0, i, lab, lens_b, lab.shape[1], ids, d["id"][:, 1].numpy())
+    out2, npred2, nrec2 = chop_fastq([str(cdir / "0")], str(fq_path), params, output_prefix=str(tmp_path / "out2"))
+    assert (npred2, nrec2) == (want_pred, want_rec)
+    assert gzip.open(out2, "rb").read().decode() == want
+    size_pt = sum(os.path.getsize(pdir / "0" / f) for f in os.listdir(pdir / "0"))
+    size_c = sum(os.path.getsize(cdir / "0" / f) for f in os.listdir(cdir / "0"))
+    assert size_c * 50 < size_pt
     if not ocq and chop_type == "all":
         assert "|T\n" in got and "|I\n" in got                   # the planted set exercises both chop kinds
 
