@@ -15,7 +15,7 @@ EXPORTS = [
     "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
     "dcb200_kernel_kind_name", "dcb200_chop_write_bgzf",
-    "dcb200_read_file_inflate", "dcb200_free",
+    "dcb200_read_file_inflate", "dcb200_free", "dcb200_ctx_set_option", "dcb200_ctx_get_option",
 ]
 
 
@@ -67,6 +67,9 @@ def lib():
     l.dcb200_ctx_stream.restype = vp
     l.dcb200_ctx_launch_count.argtypes = [vp]
     l.dcb200_ctx_launch_count.restype = i64
+    l.dcb200_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
+    l.dcb200_ctx_get_option.argtypes = [vp, C.c_char_p]
+    l.dcb200_ctx_get_option.restype = i64
     l.dcb200_encode_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     l.dcb200_weights_create.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(vp)]
     l.dcb200_weights_destroy.argtypes = [vp]
@@ -91,7 +94,7 @@ def lib():
     l.dcb200_predict_batch_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, pp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("dcb200_last_error", "dcb200_chop_params_default", "dcb200_ctx_stream", "dcb200_ctx_launch_count",
-                        "dcb200_kernel_kind_name"):
+                        "dcb200_kernel_kind_name", "dcb200_ctx_get_option", "dcb200_free"):
             getattr(l, name).restype = C.c_int
     _lib = l
     return l
@@ -126,6 +129,13 @@ class Context:
     @property
     def launches(self) -> int:
         return int(lib().dcb200_ctx_launch_count(self._h))
+
+    def set_option(self, name: str, value: int):
+        """dcb200_ctx_set_option, e.g. ``fft_min_len`` (which long-convolution kernel a batch length takes)."""
+        check(lib().dcb200_ctx_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        return int(lib().dcb200_ctx_get_option(self._h, name.encode()))
 
     def profile(self, enable: bool = True):
         check(lib().dcb200_ctx_profile(self._h, 1 if enable else 0))

@@ -20,14 +20,6 @@ from .smooth import CHOP_TYPES, MIN_READ_LEN, _ID_TABLE, smooth_chop_device
 from .writer import COMPACT_SUFFIX, IGNORE, list_batches, read_batch_compact
 
 
-@dataclass
-class ReadResult:
-    seq: str                 # decoded from the prediction tensor (non-ACGT -> N), src/smooth/predict.rs:301
-    n: int
-    is_truncated: bool
-    logits_ref: Tuple[int, int, int]   # (batch index, row, first column) to re-run with the FASTQ qual length
-
-
 def write_chopped_fastq(path: str, ix: FastqIndex, has_pred: np.ndarray, pseq_ptr: np.ndarray, pseq_len: np.ndarray,
                         action: np.ndarray, n_adapter: np.ndarray, adapter_iv: np.ndarray, n_keep: np.ndarray,
                         keep_iv: np.ndarray, threads: int = 0, level: int = 6) -> Tuple[int, int]:
@@ -69,37 +61,79 @@ def _read_spans(target: np.ndarray):
     return first, lens
 
 
-def load_prediction_batches(paths: Iterable[str], max_batches: Optional[int] = None):
+def list_prediction_files(paths: Iterable[str], max_batches: Optional[int] = None) -> List[str]:
+    """``--pdt`` arguments -> prediction files: a directory is walked recursively (src/smooth/predict.rs:219-226) and
+    truncated to ``max_batches`` files PER directory like ``load_predicts_from_batch_pts(.., max_predicts)``."""
     files: List[str] = []
     for p in paths:
-        files += list_batches(p) if os.path.isdir(p) else [p]
-    if max_batches is not None:
-        files = files[:max_batches]
-    batches = []
-    for f in files:
+        if os.path.isdir(p):
+            fs = list_batches(p)
+            files += fs[:max_batches] if max_batches is not None else fs
+        else:
+            files.append(p)
+    return files
+
+
+def iter_prediction_batches(paths: Iterable[str], max_batches: Optional[int] = None):
+    """One decoded prediction batch at a time (``.pt`` dict or compact sidecar).  A generator: a batch's tensors
+    (28 bytes per token in the reference's layout) are dropped before the next file is read; a file that fails to load
+    is reported and skipped like src/smooth/predict.rs:246-256."""
+    for f in list_prediction_files(paths, max_batches):
         try:
             d = read_batch_compact(f) if f.endswith(COMPACT_SUFFIX) else torch.load(f, map_location="cpu")
-        except Exception as e:  # noqa: BLE001  (src/smooth/predict.rs:246-256: report and skip)
+        except Exception as e:  # noqa: BLE001
             print(f"load pt {f} fail caused by Error: {e!r}")
             continue
-        batches.append(d)
-    return batches
+        yield d
+
+
+def load_prediction_batches(paths: Iterable[str], max_batches: Optional[int] = None):
+    """Eager form of :func:`iter_prediction_batches` (small inputs / tests)."""
+    return list(iter_prediction_batches(paths, max_batches))
+
+
+def _decode_pt_batch(d) -> Tuple[np.ndarray, np.ndarray, List[str], np.ndarray, np.ndarray, np.ndarray]:
+    """A ``.pt`` dict -> (row starts into the flat logits, kept lengths, ids, truncated flags, flat predicted-sequence
+    letters, letter offsets).  Mirrors src/smooth/predict.rs:263-317 minus the argmax (fused into the GPU kernel)."""
+    target = d["target"].to(torch.int64).numpy()
+    idarr = d["id"].to(torch.int64).numpy()
+    B, L = target.shape
+    first, lens = _read_spans(target)
+    n_id = np.clip(idarr[:, 0], 0, idarr.shape[1] - 2)
+    idb = idarr[:, 2:].astype(np.uint8)
+    ids = [idb[b, :n_id[b]].tobytes().decode("latin1") for b in range(B)]
+    truncated = idarr[:, 1] != 0
+    # sequence decoded from the prediction batch's tokens (non-ACGT -> N), src/smooth/predict.rs:301; only the reads'
+    # own spans are kept (1 byte per base), the [B, L] int64 tensors die with `d`
+    seq = d["seq"].numpy()
+    cols = np.arange(L)[None, :]
+    mask = (cols >= first[:, None]) & (cols < (first + lens)[:, None])
+    toks = seq[mask]
+    letters = np.ascontiguousarray(_ID_TABLE[np.where((toks >= 0) & (toks < 256), toks, 0).astype(np.uint8)])
+    loff = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
+    starts = np.arange(B, dtype=np.int64) * L + first
+    return starts, lens, ids, truncated, letters, loff
 
 
 def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None, output_prefix: Optional[str] = None,
                max_batch_size: Optional[int] = None, device: int = 0, batches=None, threads: int = 0,
-               level: int = 6) -> Tuple[str, int, int]:
-    """src/bin/predict.rs:197-384.  Returns (output path, #predictions, #records written)."""
+               level: int = 6, suffix: str = "gz", verbose: bool = False,
+               strict_ids: bool = False) -> Tuple[str, int, int]:
+    """src/bin/predict.rs:197-384.  Returns (output path, #predictions, #records written).
+
+    Prediction files are consumed one at a time (per read only the chop decision, its <= 20 intervals and one byte per
+    base of predicted sequence survive a batch); the FASTQ text is held whole, like the id -> Predict map the reference
+    holds whole (src/bin/predict.rs:222-235)."""
+    import time
+    t_start = time.time()
     params = params or ChopParams.default()
     dev = torch.device("cuda", device)
-    batches = batches if batches is not None else load_prediction_batches(predicts, max_batch_size)
-    # ---- FASTQ index (id -> quality length) ------------------------------------------------------------
+    it = iter(batches) if batches is not None else iter_prediction_batches(predicts, max_batch_size)
+    # ---- FASTQ index (id -> row, quality length) --------------------------------------------------------
     buf = read_fastq_bytes(fq)
     ix = index_fastq(buf)
-    fq_ids = [ix.name(r) for r in range(len(ix))]
-    qlen_of = {rid: int(ix.qual_len[r]) for r, rid in enumerate(fq_ids)}
-    # ---- predictions: GPU argmax + smooth + intervals + chop coordinates per batch --------------------
     R = len(ix)
+    fq_ids = [ix.name(r) for r in range(R)]
     row_of = {rid: r for r, rid in enumerate(fq_ids)}
     approved = int(params.approved_interval_number)
     has_pred = np.zeros(R, np.uint8)
@@ -113,7 +147,10 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
     keepalive = []
     n_pred_ids = set()
     pseq_fastq = None          # predicted sequence of compact batches = the normalised FASTQ sequence (ACGT, else N)
-    for d in batches:
+    n_batches = 0
+    # ---- predictions: GPU argmax + smooth + intervals + chop coordinates, one batch at a time ---------------
+    for d in it:
+        n_batches += 1
         if d.get("compact"):
             # compact sidecar: labels only; the sequence the reference decodes from the prediction tensor's tokens is a
             # function of the FASTQ sequence itself (tokenizer: A C G T -> 7..10, anything else -> N / UNK -> 'N')
@@ -126,64 +163,45 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
             ids = d["ids"]
             offs = d["offsets"]
             lens = np.diff(offs).astype(np.int32)
-            qual_lens = np.array([qlen_of.get(i, int(l)) for i, l in zip(ids, lens)], dtype=np.int32)
-            n_ad, ad, n_keep, keep, act = smooth_chop_device(
-                torch.from_numpy(d["labels"]).to(dev), torch.from_numpy(offs[:-1].astype(np.int64)).to(dev),
-                torch.from_numpy(lens).to(dev), params, torch.from_numpy(qual_lens).to(dev), logits=False)
-            n_ad, ad, n_keep, keep, act = (t.cpu().numpy() for t in (n_ad, ad, n_keep, keep, act))
-            n_pred_ids.update(ids)
-            for b, rid in enumerate(ids):
-                r = row_of.get(rid)
-                if r is None:
-                    continue
-                has_pred[r] = 1
-                action[r] = act[b]
-                n_ad_all[r] = n_ad[b]
-                n_keep_all[r] = n_keep[b]
-                ad_all[r, :ad.shape[1]] = ad[b]
-                keep_all[r, :keep.shape[1]] = keep[b]
-                pseq_ptr[r] = pseq_fastq.ctypes.data + int(ix.seq_off[r])
-                pseq_len[r] = lens[b]
-            continue
-        pred = d["prediction"].float().contiguous()
-        target = d["target"].to(torch.int64).numpy()
-        seq = d["seq"].to(torch.int64).numpy()
-        idarr = d["id"].to(torch.int64).numpy()
-        B, L = target.shape
-        first, lens = _read_spans(target)
-        ids = []
-        for b in range(B):
-            n_id = int(idarr[b, 0])
-            ids.append(bytes(idarr[b, 2:2 + n_id].astype(np.uint8)).decode("latin1"))
-        qual_lens = np.array([qlen_of.get(i, int(l)) for i, l in zip(ids, lens)], dtype=np.int32)
-        starts = (np.arange(B, dtype=np.int64) * L + first)
+            starts = offs[:-1].astype(np.int64)
+            dev_in = torch.from_numpy(d["labels"]).to(dev)
+            is_logits = False
+            letters = None
+        else:
+            starts, lens, ids, _trunc, letters, loff = _decode_pt_batch(d)
+            dev_in = d["prediction"].float().contiguous().to(dev)
+            is_logits = True
+            keepalive.append(letters)
+        rows = np.fromiter((row_of.get(i, -1) for i in ids), dtype=np.int64, count=len(ids))
+        if strict_ids and (rows < 0).any():
+            raise KeyError(f"id not found: {ids[int(np.flatnonzero(rows < 0)[0])]}")      # src/cli.rs:95
+        qual_lens = np.where(rows >= 0, ix.qual_len[np.maximum(rows, 0)], lens).astype(np.int32)
         n_ad, ad, n_keep, keep, act = smooth_chop_device(
-            pred.to(dev), torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev), params,
-            torch.from_numpy(qual_lens).to(dev), logits=True)
+            dev_in, torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev), params,
+            torch.from_numpy(qual_lens).to(dev), logits=is_logits)
         n_ad, ad, n_keep, keep, act = (t.cpu().numpy() for t in (n_ad, ad, n_keep, keep, act))
-        # sequence decoded from the prediction tensor (non-ACGT -> N), src/smooth/predict.rs:301
-        letters = np.ascontiguousarray(_ID_TABLE[np.where((seq >= 0) & (seq < 256), seq, 0).astype(np.uint8)])
-        keepalive.append(letters)
-        base = letters.ctypes.data
+        del dev_in, d
         n_pred_ids.update(ids)
-        for b, rid in enumerate(ids):          # a later batch overrides an earlier one, like the reference's HashMap
-            r = row_of.get(rid)
-            if r is None:
-                continue
-            has_pred[r] = 1
-            action[r] = act[b]
-            n_ad_all[r] = n_ad[b]
-            n_keep_all[r] = n_keep[b]
-            ad_all[r, :ad.shape[1]] = ad[b]
-            keep_all[r, :keep.shape[1]] = keep[b]
-            pseq_ptr[r] = base + int(b) * L + int(first[b])
-            pseq_len[r] = lens[b]
+        sel = rows >= 0                        # a later batch overrides an earlier one, like the reference's HashMap
+        r = rows[sel]
+        has_pred[r] = 1
+        action[r] = act[sel]
+        n_ad_all[r] = n_ad[sel]
+        n_keep_all[r] = n_keep[sel]
+        if ad.shape[1]:
+            ad_all[r, :ad.shape[1]] = ad[sel]
+        keep_all[r, :keep.shape[1]] = keep[sel]
+        if letters is None:
+            pseq_ptr[r] = np.uint64(pseq_fastq.ctypes.data) + ix.seq_off[r].astype(np.uint64)
+        else:
+            pseq_ptr[r] = np.uint64(letters.ctypes.data) + loff[:-1][sel].astype(np.uint64)
+        pseq_len[r] = lens[sel]
     if len(row_of) != R:                        # duplicated FASTQ ids: every occurrence gets the id's prediction
-        for r, rid in enumerate(fq_ids):
-            src = row_of[rid]
-            if src != r and has_pred[src]:
-                has_pred[r], action[r], n_ad_all[r], n_keep_all[r] = 1, action[src], n_ad_all[src], n_keep_all[src]
-                ad_all[r], keep_all[r], pseq_ptr[r], pseq_len[r] = ad_all[src], keep_all[src], pseq_ptr[src], pseq_len[src]
+        src = np.fromiter((row_of[i] for i in fq_ids), dtype=np.int64, count=R)
+        dup = (src != np.arange(R)) & (has_pred[src] != 0)
+        for arr in (has_pred, action, n_ad_all, n_keep_all, ad_all, keep_all, pseq_ptr, pseq_len):
+            arr[dup] = arr[src[dup]]
+    t_pred = time.time()
     # ---- FASTQ order: assemble records + BGZF on host threads (native) --------------------------------------
     if output_prefix:
         out_dir = os.path.dirname(output_prefix) or "."
@@ -192,13 +210,75 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
         out_dir = os.getcwd()                                 # the reference names the output relative to the CWD
         stem = os.path.splitext(os.path.basename(fq))[0]      # Path::file_stem (src/bin/predict.rs:349)
     tmp = os.path.join(out_dir, f".deepchopper_temp_{os.getpid()}.fq.gz")
-    n_out, _ = write_chopped_fastq(tmp, ix, has_pred, pseq_ptr, pseq_len, action, n_ad_all, ad_all, n_keep_all, keep_all,
-                                   threads=threads, level=level)
-    out = f"{stem}.{len(n_pred_ids)}pd.{n_out}record.chop.fq.gz"
+    n_out, n_text = write_chopped_fastq(tmp, ix, has_pred, pseq_ptr, pseq_len, action, n_ad_all, ad_all, n_keep_all, keep_all,
+                                        threads=threads, level=level)
+    out = f"{stem}.{len(n_pred_ids)}pd.{n_out}record.chop.fq.{suffix}"
     if not output_prefix:
         out = os.path.join(os.getcwd(), out) if not os.path.isabs(out) else out
     os.replace(tmp, out)
+    if verbose:                                               # src/bin/predict.rs:369-381 logs wall time and peak RSS
+        import resource
+        rss = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
+        print(f"chop: {n_batches} prediction batches, {len(n_pred_ids)} predictions, {R} FASTQ records -> {n_out} records, "
+              f"{n_text} text bytes; smooth/intervals {t_pred - t_start:.2f} s, write {time.time() - t_pred:.2f} s, "
+              f"peak RSS {rss:.0f} MB")
     return out, len(n_pred_ids), n_out
+
+
+# ---- PyO3-named entry points (src/python.rs:879-958) ---------------------------------------------------------
+
+def load_predicts_from_batch_pt(pt_path, ignore_label: int = IGNORE):
+    """``deepchopper.load_predicts_from_batch_pt(pt_path, ignore_label)`` (src/smooth/predict.rs:263-317):
+    ``{id: Predict}`` of one ``.pt`` batch -- argmax over the 2 classes (ties -> 0), positions whose target equals
+    ``ignore_label`` dropped, tokens decoded to ACGTN, id and truncation flag from the ``id`` row."""
+    from .smooth import Predict
+    d = torch.load(os.fspath(pt_path), map_location="cpu")
+    pred = d["prediction"]
+    target = d["target"].to(torch.int64).numpy()
+    seq = d["seq"].to(torch.int64).numpy()
+    idarr = d["id"].to(torch.int64).numpy()
+    lab = (pred[..., 1] > pred[..., 0]).to(torch.int8).numpy()        # argmax(2), first index wins a tie
+    out = {}
+    for b in range(target.shape[0]):
+        keep = target[b] != ignore_label                              # summary_predict_generic (src/utils.rs:9-31)
+        n_id = int(idarr[b, 0])
+        rid = bytes(idarr[b, 2:2 + n_id].astype(np.uint8)).decode("latin1")
+        toks = seq[b][keep]
+        letters = _ID_TABLE[np.where((toks >= 0) & (toks < 256), toks, 0).astype(np.uint8)].tobytes().decode("ascii")
+        out[rid] = Predict(lab[b][keep].tolist(), letters, rid, bool(idarr[b, 1] != 0), None)
+    return out
+
+
+def load_predicts_from_batch_pts(pt_path, ignore_label: int = IGNORE, max_predicts: Optional[int] = None):
+    """``deepchopper.load_predicts_from_batch_pts(pt_path, ignore_label=-100, max_predicts=None)``
+    (src/smooth/predict.rs:212-261): every ``.pt`` under ``pt_path`` (first ``max_predicts`` files), merged; a file that
+    fails to load is reported and skipped."""
+    files = [f for f in list_batches(os.fspath(pt_path)) if f.endswith(".pt")]
+    if max_predicts is not None:
+        files = files[:max_predicts]
+    out = {}
+    for f in files:
+        try:
+            out.update(load_predicts_from_batch_pt(f, ignore_label))
+        except Exception as e:  # noqa: BLE001
+            print(f"load pt {f} fail caused by Error: {e!r}")
+    return out
+
+
+def predict_cli(predicts, fq, smooth_window_size: int = 21, min_interval_size: int = 13,
+                approved_interval_number: int = 20, max_process_intervals: int = 4,
+                min_read_length_after_chop: int = 20, output_chopped_seqs: bool = False, chop_type: str = "all",
+                threads: Optional[int] = 2, output_prefix: Optional[str] = None,
+                max_batch_size: Optional[int] = None) -> None:
+    """``deepchopper.predict_cli`` (src/python.rs:827-876 -> src/cli.rs:57-165): the older, non-streaming chop entry.
+    Same arithmetic as ``deepchopper-chop``; the output is named ``{prefix|stem}.{n}pd.{m}record.chop.fq.bgz`` and a
+    prediction whose id is not in the FASTQ is an error (``id not found``, src/cli.rs:95).  The reference emits the
+    records in hash-map order; here they come out in FASTQ order."""
+    p = params_from_cli(smooth_window_size, min_interval_size, approved_interval_number, max_process_intervals,
+                        min_read_length_after_chop, output_chopped_seqs, chop_type)
+    predicts = [os.fspath(x) for x in ([predicts] if isinstance(predicts, (str, os.PathLike)) else predicts)]
+    chop_fastq(predicts, os.fspath(fq), p, output_prefix, max_batch_size, threads=threads or 0, suffix="bgz",
+               strict_ids=True)
 
 
 def params_from_cli(smooth_window=21, min_interval_size=13, approved_intervals=20, max_process_intervals=4,

@@ -82,7 +82,7 @@ def cmd_chop(args):
     p = params_from_cli(args.smooth_window, args.min_interval_size, args.approved_intervals, args.max_process_intervals,
                         args.min_read_length, args.output_chopped, args.chop_type)
     out, npred, nrec = chop_fastq(args.predicts, args.fq, p, args.output, args.max_batch, threads=args.threads,
-                                  level=args.compression_level)
+                                  level=args.compression_level, verbose=args.verbose)
     print(f"Wrote {nrec} records to {out} ({npred} predictions)")
 
 
@@ -123,6 +123,7 @@ def build_parser():
                     help="BGZF deflate level 1-9 (6 = the reference's default); 0 = Huffman-only, ~8x faster, ~5 %% larger")
     ch.add_argument("--output", "-o", default=None)
     ch.add_argument("--max-batch", type=int, default=None)
+    ch.add_argument("--verbose", "-v", action="store_true")     # cli.py:155-198 / src/bin/predict.rs:76-77
     ch.set_defaults(fn=cmd_chop)
     return ap
 

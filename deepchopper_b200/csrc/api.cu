@@ -1,6 +1,8 @@
 // extern "C" surface of libdcb200 (see include/dcb200.h).
 #include "common.cuh"
 
+#include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dcb {
@@ -90,8 +92,30 @@ int dcb200_ctx_create(int device, void* stream, dcb200_ctx** out) {
     }
     ctx->owns_stream = true;
   }
+  if (const char* te = getenv("DCB200_TRACE")) {  // kernel timeline tracer (tools/trace_*.py), read once per ctx
+    if (!strcmp(te, "inproj")) ctx->trace_kind = TRACE_INPROJ;
+    else if (!strcmp(te, "block")) ctx->trace_kind = TRACE_BLOCK;
+    else if (!strcmp(te, "toeplitz")) ctx->trace_kind = TRACE_TOEPLITZ;
+  }
   *out = ctx;
   return DCB200_OK;
+}
+
+int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value) {
+  DCB_ARG(ctx && name);
+  if (!strcmp(name, "fft_min_len")) {
+    DCB_ARG(value >= 0 && value <= INT_MAX);
+    ctx->fft_min_len = (int)value;
+    return DCB200_OK;
+  }
+  set_error("unknown ctx option '%s'", name);
+  return DCB200_EINVAL;
+}
+
+int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name) {
+  if (!ctx || !name) return -1;
+  if (!strcmp(name, "fft_min_len")) return ctx->fft_min_len;
+  return -1;
 }
 
 int dcb200_ctx_destroy(dcb200_ctx* ctx) {
@@ -140,6 +164,7 @@ int dcb200_forward(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok,
                    int32_t L, float* logits, uint8_t* labels) {
   DCB_ARG(ctx && w && tok && qual);
   DCB_ARG(B > 0 && L > 0 && L % 128 == 0 && L <= 32768);
+  DCB_ARG((int64_t)B * L <= INT_MAX / 2);  // token indices are 32-bit inside the kernels
   DCB_CUDA(cudaSetDevice(ctx->device));
   return forward_device(ctx, w, tok, qual, B, L, logits, labels, 1 << 30);
 }
@@ -148,6 +173,7 @@ int dcb200_forward_debug(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t
                          int32_t L, float* logits, uint8_t* labels, int32_t stop_stage) {
   DCB_ARG(ctx && w && tok && qual);
   DCB_ARG(B > 0 && L > 0 && L % 128 == 0 && L <= 32768);
+  DCB_ARG((int64_t)B * L <= INT_MAX / 2);
   DCB_CUDA(cudaSetDevice(ctx->device));
   DCB_CHECK(forward_device(ctx, w, tok, qual, B, L, logits, labels, stop_stage));
   DCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -195,7 +221,7 @@ int dcb200_ctx_profile_read(dcb200_ctx* ctx, double* ms, int64_t* counts, int32_
 }
 
 const char* dcb200_kernel_kind_name(int32_t kind) {
-  static const char* names[K_NKINDS] = {"encode", "embed_ln", "in_proj", "hyena_conv", "out_proj", "fc1", "fc2",
+  static const char* names[K_NKINDS] = {"encode", "embed_ln", "in_proj", "fft_conv", "out_proj", "fc1", "fc2",
                                         "head1", "head2", "smooth_chop", "other", "shortconv_gate", "toeplitz_conv", "mlp", "block"};
   return (kind >= 0 && kind < K_NKINDS) ? names[kind] : nullptr;
 }
@@ -342,8 +368,11 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   if (qual_lens) DCB_CHECK(stage_in(ctx, "p_qlens", qual_lens, (size_t)R * 4, &d_ql));
   // label-row starts: read r occupies columns [Lpad-len-1, Lpad-1) of row r (left pad, SEP last)
   std::vector<int64_t> st(R);
+  DCB_ARG((int64_t)R * Lrow <= INT_MAX / 2);
   for (int r = 0; r < R; ++r) {
     DCB_ARG(len[r] >= 0 && len[r] + 1 <= Lpad);
+    // a bad offset from across the plain-pointer ABI must not become an out-of-bounds device read
+    DCB_ARG(seq_off[r] >= 0 && seq_off[r] + len[r] <= n_bytes && qual_off[r] >= 0 && qual_off[r] + len[r] <= n_bytes);
     st[r] = (int64_t)r * Lrow + (Lpad - 1 - len[r]);
   }
   DCB_CHECK(stage_in(ctx, "p_starts", st.data(), (size_t)R * 8, &d_st));

@@ -68,6 +68,10 @@ struct DevBuf {
 
 namespace dcb {
 enum KernelKind { K_ENCODE = 0, K_EMBED, K_INPROJ, K_CONV, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_SMOOTH, K_OTHER, K_SCONV, K_TOEP, K_MLP, K_BLOCK, K_NKINDS };
+enum TraceKind { TRACE_NONE = 0, TRACE_INPROJ, TRACE_BLOCK, TRACE_TOEPLITZ };
+// Reads at least this long take the blocked FFT long convolution (lconv.cu), shorter ones the tensor-core Toeplitz
+// kernel (toeplitz.cu); measured crossover, see profiles/r02_summary.md
+constexpr int kDefaultFftMinLen = 6144;
 struct ProfRec {
   int kind;
   cudaEvent_t a, b;
@@ -80,6 +84,10 @@ struct dcb200_ctx {
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   int64_t launches = 0;
+  // options (dcb200_ctx_set_option); the trace kind comes from DCB200_TRACE, read once when the ctx is created
+  int fft_min_len = dcb::kDefaultFftMinLen;
+  int trace_kind = dcb::TRACE_NONE;
+  bool traced_once = false;
   // named workspaces (activations, staging), grow-only
   std::map<std::string, dcb::DevBuf> ws;
   dcb::DevBuf& buf(const char* name) { return ws[name]; }

@@ -5,9 +5,11 @@
 // tokenize_and_align_labels_and_quals_ids (deepchopper/models/llm/tokenizer.py:145-178) ->
 // DataCollatorForTokenClassificationWithQual (tokenizer.py:34-93, LEFT pad 4 / 0.0).
 //
-// One warp per read.  Pass 1: exact integer sum of squares of (q-33) (so the L2 norm is the
-// correctly rounded fp32 value of the exact sum).  Pass 2: each lane produces 4 consecutive output
-// columns: one 32-bit token store and one float4 quality store, both row-aligned and coalesced.
+// One CTA per read (grid-stride).  The read's sequence and quality strings are staged in shared memory with coalesced,
+// 16-byte aligned vector loads (the strings sit at arbitrary byte offsets of the FASTQ buffer: the copy starts at the
+// aligned address below each string).  Pass 1: exact integer sum of squares of (q-33), four bytes per shared-memory
+// word (so the L2 norm is the correctly rounded fp32 value of the exact sum).  Pass 2: each thread produces 4
+// consecutive output columns: one 32-bit token store and one float4 quality store, both row-aligned and coalesced.
 #include "common.cuh"
 
 namespace dcb {
@@ -28,31 +30,66 @@ __device__ __forceinline__ uint32_t base_to_token(uint32_t c) {
   }
 }
 
-__global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ seq_off,
-                                                     const int64_t* __restrict__ qual_off, const int32_t* __restrict__ len,
-                                                     int32_t R, int32_t Lpad, int32_t Lrow,
-                                                     uint8_t* __restrict__ tok, float* __restrict__ qual) {
-  const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
-  for (int r = warp; r < R; r += nwarps) {
+constexpr int kEncThreads = 256;
+
+__global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ seq_off,
+                                                             const int64_t* __restrict__ qual_off, const int32_t* __restrict__ len,
+                                                             int32_t R, int32_t Lpad, int32_t Lrow, int32_t cap16,
+                                                             uint8_t* __restrict__ tok, float* __restrict__ qual) {
+  extern __shared__ uint4 enc_smem[];   // [2][cap16] 16-byte words: sequence, quality
+  __shared__ unsigned long long red[kEncThreads / 32];
+  __shared__ float nrm_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
     const int n = len[r];
-    const uint8_t* s = bytes + seq_off[r];
-    const uint8_t* q = bytes + qual_off[r];
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(bytes + seq_off[r]);
+    const uintptr_t qa = reinterpret_cast<uintptr_t>(bytes + qual_off[r]);
+    const int smis = (int)(sa & 15), qmis = (int)(qa & 15);
+    const uint4* sg = reinterpret_cast<const uint4*>(sa - smis);
+    const uint4* qg = reinterpret_cast<const uint4*>(qa - qmis);
+    const int ns16 = (n + smis + 15) >> 4, nq16 = (n + qmis + 15) >> 4;
+    // interior 16-byte words with vector loads; the first and last word of a string byte by byte, so that nothing
+    // outside [string, string + n) is ever read (the strings may touch the ends of the caller's buffer)
+    auto stage = [&](const uint4* g, int mis, int n16, uint4* dst) {
+      for (int i = tid; i < n16; i += kEncThreads) {
+        if (i > 0 && i < n16 - 1) {
+          dst[i] = __ldg(g + i);
+        } else {
+          const uint8_t* gb = reinterpret_cast<const uint8_t*>(g + i);
+          uint8_t* db = reinterpret_cast<uint8_t*>(dst + i);
+          for (int b = 0; b < 16; ++b) {
+            const int pos = 16 * i + b - mis;  // index into the string
+            db[b] = (pos >= 0 && pos < n) ? __ldg(gb + b) : (uint8_t)0;
+          }
+        }
+      }
+    };
+    stage(sg, smis, ns16, enc_smem);
+    stage(qg, qmis, nq16, enc_smem + cap16);
+    __syncthreads();
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(enc_smem) + smis;
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(enc_smem + cap16) + qmis;
     // pass 1: ||q-33||^2, exact in 64-bit integers
     unsigned long long acc = 0;
-    for (int i = lane; i < n; i += 32) {
-      int v = (int)q[i] - 33;
+    for (int i = tid; i < n; i += kEncThreads) {
+      const int v = (int)q[i] - 33;
       acc += (unsigned long long)(v * v);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    float nrm = sqrtf((float)acc);               // F.normalize: x / max(||x||_2, eps), tokenizer.py:167
-    nrm = fmaxf(nrm, 1e-12f);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t = 0;
+      for (int w = 0; w < kEncThreads / 32; ++w) t += red[w];
+      nrm_s = fmaxf(sqrtf((float)t), 1e-12f);    // F.normalize: x / max(||x||_2, eps), tokenizer.py:167
+    }
+    __syncthreads();
+    const float nrm = nrm_s;
     const int pad = Lpad - (n + 1);
     uint32_t* trow = reinterpret_cast<uint32_t*>(tok + (int64_t)r * Lrow);
     float4* qrow = reinterpret_cast<float4*>(qual + (int64_t)r * Lrow);
-    for (int c4 = lane; c4 < Lrow / 4; c4 += 32) {
+    for (int c4 = tid; c4 < Lrow / 4; c4 += kEncThreads) {
       uint32_t tw = 0;
       float qv[4];
 #pragma unroll
@@ -73,18 +110,22 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t* __restrict__
       trow[c4] = tw;
       qrow[c4] = make_float4(qv[0], qv[1], qv[2], qv[3]);
     }
+    __syncthreads();   // the staging buffers are reused by the next read
   }
 }
 
 int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
                   const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual) {
   if (R == 0) return DCB200_OK;
-  const int threads = 256;
-  int blocks = (R + 7) / 8;
-  const int cap = ctx->sm_count * 8 * 4;
+  // staging: two strings of at most Lpad - 1 bytes, each with up to 15 bytes of alignment slack on either side
+  const int cap16 = (Lpad + 15 + 15) / 16 + 1;
+  const size_t smem = (size_t)2 * cap16 * sizeof(uint4);
+  DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&encode_kernel), smem > 48 * 1024 ? smem : 48 * 1024));
+  int blocks = R;
+  const int cap = ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
   ProfScope prof(ctx, K_ENCODE);
-  encode_kernel<<<blocks, threads, 0, ctx->stream>>>(bytes, seq_off, qual_off, len, R, Lpad, Lrow, tok, qual);
+  encode_kernel<<<blocks, kEncThreads, smem, ctx->stream>>>(bytes, seq_off, qual_off, len, R, Lpad, Lrow, cap16, tok, qual);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }

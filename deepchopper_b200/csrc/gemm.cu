@@ -1,4 +1,5 @@
-// Persistent, warp-specialised tcgen05 GEMMs with fused epilogues for the Hyena layers and the head.
+// Persistent, warp-specialised tcgen05 GEMMs with fused epilogues for the classification head (the Hyena layers'
+// projections live in inproj.cu and block.cu).
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a 3/4-stage smem ring
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128/256, K=16) into TMEM
@@ -9,10 +10,6 @@
 //               warp fills the other TMEM accumulator stage
 //
 // Modes (reference ops they replace, SURVEY Appendix A / K3,K6,K7,K8):
-//   INPROJ   z^T = W_in . LN1(h)^T + b      -> bf16 channel-major [B,768,L]  (operand roles swapped so
-//            the accumulator rows are channels and a thread writes contiguous tokens)
-//   OUTPROJ  h' = y . W_o^T + b + h ; m = LN2(h')   (A = y read MN-major straight from the conv's
-//            channel-major output: no transpose pass)
 //   HEAD1    r = relu(hf . Wh1^T + b1) + q  -> bf16 [T,1024]        (head.py:94-97)
 //   HEAD2    o = relu(r . Wh2^T + b2 + r) ; logits = o . W3^T + b3 ; label = l1 > l0   (head.py:98-102)
 #include "common.cuh"
@@ -32,10 +29,8 @@ constexpr int kStageBytes = 32 * kStagePitch;       // per epilogue warp
 constexpr int kVecFloats = 3 * 1024;                // column vectors cached in smem (bias / LN gamma,beta / linear3)
 
 template <int MODE> struct Traits;
-template <> struct Traits<G_INPROJ>  { static constexpr int K = 256,  NT = 128, INNER = 6, STAGES = 4; static constexpr bool A_MN = false; };
-template <> struct Traits<G_OUTPROJ> { static constexpr int K = 256,  NT = 256, INNER = 1, STAGES = 3; static constexpr bool A_MN = true;  };
-template <> struct Traits<G_HEAD1>   { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
-template <> struct Traits<G_HEAD2>   { static constexpr int K = 1024, NT = 256, INNER = 4, STAGES = 3; static constexpr bool A_MN = false; };
+template <> struct Traits<G_HEAD1> { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; };
+template <> struct Traits<G_HEAD2> { static constexpr int K = 1024, NT = 256, INNER = 4, STAGES = 3; };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -96,13 +91,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   // column vectors -> smem (epilogue warps read them as broadcast / lane-fixed float4)
-  if (MODE == G_OUTPROJ) {
-    for (int i = threadIdx.x; i < 256; i += kThreads) {
-      vec[i] = p.bias[i];
-      vec[1024 + i] = p.ln_g[i];
-      vec[2048 + i] = p.ln_b[i];
-    }
-  } else if (MODE == G_HEAD1) {
+  if (MODE == G_HEAD1) {
     for (int i = threadIdx.x; i < 1024; i += kThreads) vec[i] = p.bias[i];
   } else if (MODE == G_HEAD2) {
     for (int i = threadIdx.x; i < 1024; i += kThreads) {
@@ -132,19 +121,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
             const uint32_t b_dst = a_dst + A_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            if (MODE == G_INPROJ) {
-              tma_load_2d(a_dst, &tmA, full_bar(stage), kc * kBlockK, i * kTileM);  // W_in rows (channels)
-              tma_load_2d(b_dst, &tmB, full_bar(stage), kc * kBlockK, tok0);        // tokens
-            } else {
-              if (Tr::A_MN) {
-                const int b = tok0 / p.L, l0 = tok0 % p.L;
-                tma_load_3d(a_dst, &tmA, full_bar(stage), l0, kc * kBlockK, b);
-                tma_load_3d(a_dst + 8192, &tmA, full_bar(stage), l0 + 64, kc * kBlockK, b);
-              } else {
-                tma_load_2d(a_dst, &tmA, full_bar(stage), kc * kBlockK, tok0);
-              }
-              tma_load_2d(b_dst, &tmB, full_bar(stage), kc * kBlockK, i * NT);
-            }
+            tma_load_2d(a_dst, &tmA, full_bar(stage), kc * kBlockK, tok0);
+            tma_load_2d(b_dst, &tmB, full_bar(stage), kc * kBlockK, i * NT);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -157,7 +135,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===== MMA issuer: the whole warp runs the loop, the elected lane issues (ptx.cuh umma_bf16_x4_e) =====
     {
       const uint32_t el = elect_one() ? 1u : 0u;
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, NT, Tr::A_MN, false);
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, NT, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -173,9 +151,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_after();
             const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
             const uint32_t b_addr = a_addr + A_BYTES;
-            // K-major tiles advance 32 B per K = 16 slice; the MN-major A tile (out_proj) 2 KB per slice
-            const uint64_t adesc0 = Tr::A_MN ? make_desc_sw128(a_addr, 8192, 1024) : make_desc_sw128(a_addr, 16, 1024);
-            umma_bf16_x4_e<1>(d_tmem, adesc0, Tr::A_MN ? 128 : 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc, kc ? 1u : 0u, el);
+            // K-major tiles advance 32 B per K = 16 slice
+            umma_bf16_x4_e<1>(d_tmem, make_desc_sw128(a_addr, 16, 1024), 2, make_desc_sw128(b_addr, 16, 1024), 2, idesc,
+                              kc ? 1u : 0u, el);
             umma_commit_e(empty_bar(stage), el);  // frees the smem slot once these MMAs retire
             if (++stage == kStages) {
               stage = 0;
@@ -207,15 +185,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     uint32_t tile_parity = 0;
     uint32_t v[32];
-    float4 rpre0[8], rpre1[8];  // LN modes: residual of the next two column chunks (T layout)
-    if (MODE == G_OUTPROJ && (int)blockIdx.x < num_outer) {  // (LN modes only)
-      const size_t r0 = (size_t)blockIdx.x * kTileM + quad * 32 + trow0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rpre0[i] = *reinterpret_cast<const float4*>(p.resid + (r0 + 4 * i) * 256 + half * HALF + piece * 4);
-        rpre1[i] = *reinterpret_cast<const float4*>(p.resid + (r0 + 4 * i) * 256 + half * HALF + piece * 4 + 32);
-      }
-    }
     for (int o = blockIdx.x; o < num_outer; o += gridDim.x) {
       const int tok0 = o * kTileM;
       float lg0[8], lg1[8];  // HEAD2 partial logits of my 8 T-layout rows
@@ -226,12 +195,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * NT + half * HALF + ((uint32_t)(quad * 32) << 16);
 
-        if (MODE == G_INPROJ || MODE == G_HEAD1) {
+        if (MODE == G_HEAD1) {
           // ---- bf16 output, element-wise epilogue: 64 columns (128 B of bf16) per staged group -------------
           const size_t own_row = (size_t)tok0 + quad * 32 + lane;
-          float rowv = 0.f;  // INPROJ: bias of my channel row; HEAD1: quality of my token row
-          if (MODE == G_INPROJ) rowv = __ldg(p.bias + it * kTileM + quad * 32 + lane);
-          if (MODE == G_HEAD1) rowv = __ldg(p.qual + own_row);
+          const float rowv = __ldg(p.qual + own_row);  // quality of my token row
 #pragma unroll 1
           for (int grp = 0; grp < HALF / 64; ++grp) {
 #pragma unroll
@@ -242,17 +209,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float y[8];
-                if (MODE == G_INPROJ) {
+                const float4 ba = b4[2 * q], bb = b4[2 * q + 1];
+                const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[q * 8 + j]) + rowv;
-                } else {
-                  const float4 ba = b4[2 * q], bb = b4[2 * q + 1];
-                  const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float x = __uint_as_float(v[q * 8 + j]) + bj[j];
-                    y[j] = fmaxf(x, 0.f) + rowv;
-                  }
+                for (int j = 0; j < 8; ++j) {
+                  const float x = __uint_as_float(v[q * 8 + j]) + bj[j];
+                  y[j] = fmaxf(x, 0.f) + rowv;
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + c * 64 + q * 16),
                              "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])),
@@ -262,17 +224,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             __syncwarp();
             // T-layout coalesced store: 4 rows x 128 B per instruction
-            __nv_bfloat16* dst;
-            size_t pitch;
-            if (MODE == G_INPROJ) {
-              const int b = tok0 / p.L, l0 = tok0 % p.L;
-              dst = p.out_bf16 + ((size_t)b * 768 + it * kTileM + quad * 32 + trow0) * p.L + l0 + half * HALF + grp * 64 +
-                    piece * 8;
-              pitch = (size_t)p.L;
-            } else {
-              dst = p.out_bf16 + ((size_t)tok0 + quad * 32 + trow0) * 1024 + it * NT + half * HALF + grp * 64 + piece * 8;
-              pitch = 1024;
-            }
+            __nv_bfloat16* dst =
+                p.out_bf16 + ((size_t)tok0 + quad * 32 + trow0) * 1024 + it * NT + half * HALF + grp * 64 + piece * 8;
+            constexpr size_t pitch = 1024;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 w = *reinterpret_cast<const uint4*>(stg_t + i * 4 * kStagePitch);
@@ -280,121 +234,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             __syncwarp();
           }
-        } else if (MODE == G_OUTPROJ) {
-          // ---- + bias + residual -> h (fp32), LayerNorm -> bf16 ------------------------------------------------
-          // Global I/O in the T layout (whole 128-byte lines per instruction); the residual of the next two
-          // column chunks is prefetched into registers (memory-level parallelism: these kernels are
-          // HBM-bound, 3-4.6 KB per token); x = acc + bias + residual goes back into the TMEM accumulator so
-          // the normalisation pass needs no second trip through L2.
-          float sum[8], sq[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
-          const size_t row_t = (size_t)tok0 + quad * 32 + trow0;  // + 4 i
-          const int colbase = half * HALF + piece * 4;
-#pragma unroll
-          for (int c = 0; c < HALF / 32; ++c) {
-            float4 (&rc)[8] = (c & 1) ? rpre1 : rpre0;
-            tmem_ld32(t_row + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + q * 16), "r"(v[4 * q]),
-                           "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
-                           : "memory");
-            __syncwarp();
-            const int col = colbase + c * 32;
-            const float4 bb = *reinterpret_cast<const float4*>(vec + col);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4* sp = reinterpret_cast<float4*>(const_cast<uint8_t*>(stg_t) + i * 4 * kStagePitch);
-              const float4 a = *sp;
-              const float4 r = rc[i];
-              float4 x;
-              x.x = a.x + bb.x + r.x;
-              x.y = a.y + bb.y + r.y;
-              x.z = a.z + bb.z + r.z;
-              x.w = a.w + bb.w + r.w;
-              *reinterpret_cast<float4*>(p.h_out + (row_t + 4 * i) * 256 + col) = x;
-              *sp = x;
-              sum[i] += (x.x + x.y) + (x.z + x.w);
-              sq[i] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, sq[i]))));
-            }
-            // prefetch the residual two chunks ahead (this tile), or the first chunks of my next tile
-            {
-              const int cn = c + 2;
-              if (cn < HALF / 32) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  rc[i] = *reinterpret_cast<const float4*>(p.resid + (row_t + 4 * i) * 256 + colbase + cn * 32);
-              } else if (o + (int)gridDim.x < num_outer) {
-                const size_t nrow = (size_t)(o + gridDim.x) * kTileM + quad * 32 + trow0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  rc[i] = *reinterpret_cast<const float4*>(p.resid + (nrow + 4 * i) * 256 + colbase + (cn - HALF / 32) * 32);
-              }
-            }
-            __syncwarp();
-            // x back to the accumulator (row-owner layout)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(v[4 * q]), "=r"(v[4 * q + 1]), "=r"(v[4 * q + 2]), "=r"(v[4 * q + 3])
-                           : "r"(stg_own + q * 16)
-                           : "memory");
-            tmem_st32(t_row + c * 32, v);
-            __syncwarp();
-          }
-          // row statistics: reduce over the 8 lanes sharing a row, then over the two column halves
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-              sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], d);
-              sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], d);
-            }
-          }
-          float2* st = stats + tile_parity * 256;
-          if (piece == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) st[half * 128 + quad * 32 + trow0 + 4 * i] = make_float2(sum[i], sq[i]);
-          }
-          tmem_st_wait();
-          named_bar_sync(1 + quad, 64);
-          const float2 sa = st[quad * 32 + lane], sb = st[128 + quad * 32 + lane];  // my own row (row-owner)
-          const float mean = (sa.x + sb.x) * (1.0f / 256.0f);
-          const float rstd = rsqrtf(fmaxf((sa.y + sb.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll 1
-          for (int grp = 0; grp < HALF / 64; ++grp) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld32(t_row + grp * 64 + c * 32, v);
-              tmem_ld_wait();
-              const float4* g4 = reinterpret_cast<const float4*>(vec + 1024 + half * HALF + grp * 64 + c * 32);
-              const float4* b4 = reinterpret_cast<const float4*>(vec + 2048 + half * HALF + grp * 64 + c * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 ga = g4[2 * q], gb = g4[2 * q + 1], ba = b4[2 * q], bb2 = b4[2 * q + 1];
-                const float gj[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb2.x, bb2.y, bb2.z, bb2.w};
-                float y[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = fmaf((__uint_as_float(v[q * 8 + j]) - mean) * rstd, gj[j], bj[j]);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + c * 64 + q * 16),
-                             "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])),
-                             "r"(pack_bf16(y[6], y[7]))
-                             : "memory");
-              }
-            }
-            __syncwarp();
-            __nv_bfloat16* dst = p.out_bf16 + row_t * 256 + half * HALF + grp * 64 + piece * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint4 w = *reinterpret_cast<const uint4*>(stg_t + i * 4 * kStagePitch);
-              *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * 256) = w;
-            }
-            __syncwarp();
-          }
-          tile_parity ^= 1;
         } else {  // G_HEAD2
           const size_t row_t = (size_t)tok0 + quad * 32 + trow0;
 #pragma unroll 1
@@ -481,8 +320,7 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
   const size_t smem = smem_bytes<MODE>();
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&gemm_kernel<MODE>), smem));
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
-  static const int kinds[4] = {K_INPROJ, K_OUTPROJ, K_HEAD1, K_HEAD2};
-  ProfScope prof(ctx, kinds[MODE]);
+  ProfScope prof(ctx, MODE == G_HEAD1 ? K_HEAD1 : K_HEAD2);
   gemm_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(a, b, p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
@@ -490,8 +328,6 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
 
 int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
   switch (mode) {
-    case G_INPROJ: return launch_mode<G_INPROJ>(ctx, a, b, p);
-    case G_OUTPROJ: return launch_mode<G_OUTPROJ>(ctx, a, b, p);
     case G_HEAD1: return launch_mode<G_HEAD1>(ctx, a, b, p);
     case G_HEAD2: return launch_mode<G_HEAD2>(ctx, a, b, p);
   }

@@ -7,18 +7,14 @@ struct dcb200_ctx;
 
 namespace dcb {
 
-enum GemmMode { G_INPROJ = 0, G_OUTPROJ = 1, G_HEAD1 = 2, G_HEAD2 = 3 };
+enum GemmMode { G_HEAD1 = 2, G_HEAD2 = 3 };
 
 struct GemmParams {
   int T;          // tokens = B * L (multiple of 128)
   int L;          // padded read length (multiple of 128)
   int num_outer;  // T / 128 token tiles
   const float* bias;
-  const float* resid;       // fp32 [T,256]          (OUTPROJ, FC2)
-  float* h_out;             // fp32 [T,256] or null  (OUTPROJ, FC2)
-  const float* ln_g;        // [256]
-  const float* ln_b;        // [256]
-  __nv_bfloat16* out_bf16;  // INPROJ: z [B,768,L]; OUTPROJ/FC2: u [T,256]; FC1: g [T,1024]; HEAD1: r [T,1024]
+  __nv_bfloat16* out_bf16;  // HEAD1: r [T,1024]
   const float* qual;        // HEAD1: [T]
   const __nv_bfloat16* r_in;  // HEAD2: r [T,1024]
   const float* w3;          // HEAD2: [2,1024]

@@ -3,18 +3,16 @@
 //   -> ln_f -> head (deepchopper/models/llm/head.py:94-102) -> logits / labels
 // Reference entry: deepchopper/models/basic_module.py:90-100 -> deepchopper/models/llm/hyena.py:29-41.
 #include "common.cuh"
-#include "fftconv.h"
 #include "block.h"
 #include "gemm.h"
 #include "inproj.h"
-#include "mlp.h"
+#include "lconv.h"
 #include "toeplitz.h"
-
-#include <stdlib.h>
 
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 
 namespace dcb {
@@ -30,13 +28,12 @@ struct LayerW {
   __nv_bfloat16 *w_in = nullptr, *w_out = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
   float *b_in = nullptr, *b_out = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
   float *short_w = nullptr, *short_b = nullptr, *filt_D = nullptr;
-  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   float* k = nullptr;  // [256][Lmax] implicit filter, evaluated once
-  std::map<int, float2*> KF;  // per FFT size N: [256][N]
   __nv_bfloat16* toep = nullptr;  // Toeplitz core-matrix table of k' (toeplitz.cu), built on first use
-  CUtensorMap tm_in, tm_in_mc, tm_out;
-  std::vector<float> hb_fc1, hb_fc2, h_ln1_g, h_ln1_b, hb_out, h_ln2_g, h_ln2_b;  // host copies: passed to kernels as constant-bank parameters
-  CUtensorMap tm_w1u, tm_w2u, tm_wou;  // per-CTA halves of the weight tiles for the fused MLP kernel (64 / 128-row boxes)
+  float4* lc_K = nullptr;         // filter spectra of the blocked FFT convolution (lconv.cu), built on first use
+  CUtensorMap tm_in_mc;
+  std::vector<float> hb_fc1, hb_fc2, hb_out;  // host copies: passed to the block kernel as constant-bank parameters
+  CUtensorMap tm_w1u, tm_w2u, tm_wou;  // per-CTA halves of the weight tiles for the block kernel (128-row boxes)
 };
 
 }  // namespace dcb
@@ -46,13 +43,13 @@ struct dcb200_weights {
   int Lmax = 0;
   float* emb = nullptr;  // [16][256]
   dcb::LayerW layer[dcb::kLayers];
-  float *lnf_g = nullptr, *lnf_b = nullptr;
-  std::vector<float> h_lnf_g, h_lnf_b;
   __nv_bfloat16 *wh1 = nullptr, *wh2 = nullptr;
   float *bh1 = nullptr, *bh2 = nullptr, *w3 = nullptr, *b3 = nullptr;
   CUtensorMap tm_h1, tm_h2;
-  std::map<int, float2*> tw;  // per FFT size N: exp(-2 pi i k/N)
   int toep_cap = 0;           // read length the Toeplitz tables were built for
+  float2* lc_tw = nullptr;    // twiddle tables of the blocked FFT convolution
+  int lc_nbK = 0;             // block distances the filter spectra cover
+  std::mutex lazy_mu;         // guards the lazily built tables above (several ctxs / threads may share the weights)
   std::vector<void*> allocs;
 };
 
@@ -105,17 +102,8 @@ __global__ void __launch_bounds__(128) implicit_filter_kernel(FilterW w, int Lma
   }
 }
 
-__global__ void twiddle_kernel(float2* tw, int N) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= N) return;
-  double s, c;
-  sincospi(2.0 * (double)k / (double)N, &s, &c);
-  tw[k] = make_float2((float)c, (float)(-s));
-}
-
 // Embedding gather + LayerNorm1 of layer 0: one warp per token (8 features per lane).
-__global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict__ tok, const float* __restrict__ emb,
-                                                       const float* __restrict__ g, const float* __restrict__ b, int T,
+__global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict__ tok, const float* __restrict__ emb, int T,
                                                        float* __restrict__ h, __nv_bfloat16* __restrict__ u) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -144,9 +132,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int col = lane * 8 + 2 * i;
-      const float y0 = fmaf((x[2 * i] - mean) * rstd, __ldg(g + col), __ldg(b + col));
-      const float y1 = fmaf((x[2 * i + 1] - mean) * rstd, __ldg(g + col + 1), __ldg(b + col + 1));
+      const float y0 = (x[2 * i] - mean) * rstd, y1 = (x[2 * i + 1] - mean) * rstd;  // affine part folded into in_linear
       __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
       o[i] = *reinterpret_cast<uint32_t*>(&r);
     }
@@ -287,16 +273,7 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.short_filter.weight", 3 * kD * 3, &lw.short_w));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.short_filter.bias", 3 * kD, &lw.short_b));
     DCB_CHECK(upload_f32(ctx, w, sd, p + "mixer.filter_fn.bias", kD, &lw.filt_D));
-    // the affine parts are folded into the following Linear: what is left of each LayerNorm is the identity affine
-    // (kept for the split / FFT cross-check kernels, which still take gain and bias vectors)
-    lw.h_ln1_g.assign(kD, 1.0f);
-    lw.h_ln1_b.assign(kD, 0.0f);
-    lw.h_ln2_g.assign(kD, 1.0f);
-    lw.h_ln2_b.assign(kD, 0.0f);
-    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln1_g, &lw.ln1_g));
-    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln1_b, &lw.ln1_b));
-    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln2_g, &lw.ln2_g));
-    DCB_CHECK(upload_f32_host(ctx, w, lw.h_ln2_b, &lw.ln2_b));
+    // (the LayerNorms' affine parts are folded into the Linear that follows each of them: the kernels only normalise)
     DCB_CHECK(upload_folded_linear(ctx, w, sd, p + "mlp.fc1.weight", p + "mlp.fc1.bias", p + "norm2.weight",
                                    p + "norm2.bias", kInner, kD, &lw.w_fc1, &lw.b_fc1, &lw.hb_fc1));
     DCB_CHECK(upload_bf16(ctx, w, sd, p + "mlp.fc2.weight", kD * kInner, &lw.w_fc2));
@@ -328,17 +305,11 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
     lw.k = static_cast<float*>(kbuf);
     implicit_filter_kernel<<<(w->Lmax + 127) / 128, 128, 0, ctx->stream>>>(fw, w->Lmax, lw.k);
     DCB_LAUNCH_CHECK(ctx);
-    DCB_CHECK(make_tmap_2d(&lw.tm_in, lw.w_in, 3 * kD, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_in_mc, lw.w_in, 3 * kD, kD, 64));  // inproj_conv: half boxes, multicast across a cluster of 2
-    DCB_CHECK(make_tmap_2d(&lw.tm_out, lw.w_out, kD, kD, 256));
     DCB_CHECK(make_tmap_2d(&lw.tm_w1u, lw.w_fc1, kInner, kD, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_w2u, lw.w_fc2, kD, kInner, 128));
     DCB_CHECK(make_tmap_2d(&lw.tm_wou, lw.w_out, kD, kD, 128));
   }
-  w->h_lnf_g.assign(kD, 1.0f);
-  w->h_lnf_b.assign(kD, 0.0f);
-  DCB_CHECK(upload_f32_host(ctx, w, w->h_lnf_g, &w->lnf_g));
-  DCB_CHECK(upload_f32_host(ctx, w, w->h_lnf_b, &w->lnf_b));
   DCB_CHECK(upload_folded_linear(ctx, w, sd, "head.linear1.weight", "head.linear1.bias", "ln_f.weight", "ln_f.bias", kInner,
                                  kD, &w->wh1, &w->bh1, nullptr));
   DCB_CHECK(upload_bf16(ctx, w, sd, "head.linear2.weight", kInner * kInner, &w->wh2));
@@ -366,52 +337,60 @@ int weights_create(dcb200_ctx* ctx, const char* const* names, const float* const
   return DCB200_OK;
 }
 
-// twiddle table + per-layer filter spectra for FFT size N (built on first use, then cached)
-static int ensure_fft_size(dcb200_ctx* ctx, dcb200_weights* w, int N) {
-  if (w->tw.count(N)) return DCB200_OK;
-  void* t = nullptr;
-  DCB_CUDA(cudaMalloc(&t, (size_t)N * 8));
-  w->allocs.push_back(t);
-  twiddle_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(static_cast<float2*>(t), N);
-  DCB_LAUNCH_CHECK(ctx);
-  const FftPlan plan = make_plan(N);
-  for (int l = 0; l < kLayers; ++l) {
-    void* kf = nullptr;
-    DCB_CUDA(cudaMalloc(&kf, (size_t)kD * N * 8));
-    w->allocs.push_back(kf);
-    DCB_CHECK(launch_filter_spectrum(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, plan,
-                                     static_cast<float2*>(t), static_cast<float2*>(kf)));
-    w->layer[l].KF[N] = static_cast<float2*>(kf);
-  }
-  w->tw[N] = static_cast<float2*>(t);
-  return DCB200_OK;
-}
 
-// Toeplitz core-matrix tables of all layers, built on first use for reads up to 8192 tokens (35 MB per layer) and
-// rebuilt for the model's full 32768 (135 MB per layer) the first time a longer batch arrives
+// Toeplitz core-matrix tables of all layers, built on first use for reads up to 8192 tokens (35 MB per layer); a longer
+// batch that still takes the Toeplitz kernel (ctx option fft_min_len raised) rebuilds them for the model's 32768.
+// The tables belong to the shared weights: the build is serialised, finished before anyone launches against it
+// (another ctx / stream may share the weights), and a superseded smaller table is released.
 static int ensure_toeplitz(dcb200_ctx* ctx, dcb200_weights* w, int L) {
+  std::lock_guard<std::mutex> lock(w->lazy_mu);
   if (w->toep_cap >= L) return DCB200_OK;
   const int cap = L <= 8192 ? 8192 : kToepMaxL;
+  DCB_CUDA(cudaDeviceSynchronize());  // nobody may still be reading a table that is about to be replaced
   for (int l = 0; l < kLayers; ++l) {
     void* t = nullptr;
     DCB_CUDA(cudaMalloc(&t, toeplitz_table_bytes(cap)));
-    w->allocs.push_back(t);  // (a superseded smaller table is released with the weights)
     DCB_CHECK(launch_toeplitz_table(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, cap,
                                     static_cast<__nv_bfloat16*>(t)));
+    if (void* old = w->layer[l].toep) {
+      for (auto& a : w->allocs)
+        if (a == old) a = t;
+      cudaFree(old);
+    } else {
+      w->allocs.push_back(t);
+    }
     w->layer[l].toep = static_cast<__nv_bfloat16*>(t);
   }
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));
   w->toep_cap = cap;
   return DCB200_OK;
 }
 
-// Which long-convolution kernel: block-Toeplitz tensor-core GEMMs up to 4096 tokens, shared-memory FFT above.
-// DCB200_CONV=fft|toeplitz overrides (used by the tests to cover both kernels at the same size).
-static bool use_toeplitz(int L) {
-  const char* e = getenv("DCB200_CONV");
-  if (e && !strcmp(e, "fft")) return false;
-  if (L > kToepMaxL) return false;
-  if (e && !strcmp(e, "toeplitz")) return true;
-  return true;
+// Twiddles + filter spectra of the blocked FFT convolution: all four block distances (the model's 32768 tokens) at the
+// first long batch, 64 KB per channel and distance (67 MB per layer).  Same sharing rules as ensure_toeplitz.
+static int ensure_lconv(dcb200_ctx* ctx, dcb200_weights* w, int L) {
+  std::lock_guard<std::mutex> lock(w->lazy_mu);
+  const int need = lconv_blocks_for(L);
+  if (w->lc_nbK >= need) return DCB200_OK;
+  const int nbK = lconv_blocks_for(lconv_max_len());
+  if (!w->lc_tw) {
+    void* t = nullptr;
+    DCB_CUDA(cudaMalloc(&t, lconv_twiddle_bytes()));
+    w->allocs.push_back(t);
+    w->lc_tw = static_cast<float2*>(t);
+    DCB_CHECK(launch_lconv_twiddles(ctx, w->lc_tw));
+  }
+  for (int l = 0; l < kLayers; ++l) {
+    void* kf = nullptr;
+    DCB_CUDA(cudaMalloc(&kf, lconv_spectrum_bytes(nbK)));
+    w->allocs.push_back(kf);
+    w->layer[l].lc_K = static_cast<float4*>(kf);
+    DCB_CHECK(launch_lconv_filter_spectrum(ctx, w->layer[l].k, w->Lmax, w->Lmax, w->layer[l].filt_D, w->lc_tw, nbK,
+                                           w->layer[l].lc_K));
+  }
+  DCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  w->lc_nbK = nbK;
+  return DCB200_OK;
 }
 
 int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
@@ -421,85 +400,73 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   do {                                 \
     if (stage++ >= stop_stage) return DCB200_OK; \
   } while (0)
-  dcb200_weights* w = const_cast<dcb200_weights*>(wc);  // lazily cached spectra
+  dcb200_weights* w = const_cast<dcb200_weights*>(wc);  // lazily built convolution tables
   if (w->device != ctx->device) {
     set_error("weights live on device %d, ctx on %d", w->device, ctx->device);
     return DCB200_EINVAL;
   }
-  const bool toep = use_toeplitz(L);
-  int N = 256;
-  while (N < 2 * L) N <<= 1;
-  if (!toep) {
-    if (conv_smem_bytes(N, L) > 227 * 1024) {
-      set_error("L=%d: the FFT fallback kernel holds at most 8192 tokens; use the default (Toeplitz) path", L);
-      return DCB200_EINVAL;
-    }
-    DCB_CHECK(ensure_fft_size(ctx, w, N));
-  } else {
-    DCB_CHECK(ensure_toeplitz(ctx, w, L));
-  }
+  // Long convolution: tensor-core Toeplitz GEMMs (MMA work grows with L) below the measured crossover, the blocked
+  // shared-memory FFT (O(L log L), fp32) above it.  ctx option "fft_min_len" moves the crossover (the tests run both
+  // kernels at the same sizes).
+  const bool fft = L >= ctx->fft_min_len;
+  if (fft) DCB_CHECK(ensure_lconv(ctx, w, L));
+  else DCB_CHECK(ensure_toeplitz(ctx, w, L));
   const size_t T = (size_t)B * L;
   DevBuf& bhA = ctx->buf("act_hA");
-  DevBuf& bhB = ctx->buf("act_hB");
   DevBuf& bu = ctx->buf("act_u");
-  DevBuf& bz = ctx->buf("act_z");
   DevBuf& by = ctx->buf("act_y");
   DevBuf& bg = ctx->buf("act_g");
+  DevBuf& bvv = ctx->buf("act_vv");
+  DevBuf& bgt = ctx->buf("act_gate");
   DCB_CHECK(bhA.reserve(T * kD * 4));
-  DCB_CHECK(bhB.reserve(T * kD * 4));
   DCB_CHECK(bu.reserve(T * kD * 2));
-  if (!toep) DCB_CHECK(bz.reserve(T * 3 * kD * 2));  // z only exists on the FFT fallback path
   DCB_CHECK(by.reserve(T * kD * 2));
   DCB_CHECK(bg.reserve(T * kInner * 2));
+  DCB_CHECK(bvv.reserve(T * kD * 2));
+  DCB_CHECK(bgt.reserve(T * kD * 2));
   float* hA = bhA.as<float>();
-  float* hB = bhB.as<float>();
   __nv_bfloat16* u = bu.as<__nv_bfloat16>();
-  __nv_bfloat16* z = bz.as<__nv_bfloat16>();
   __nv_bfloat16* y = by.as<__nv_bfloat16>();
   __nv_bfloat16* g = bg.as<__nv_bfloat16>();
+  __nv_bfloat16* vv = bvv.as<__nv_bfloat16>();
+  __nv_bfloat16* gate = bgt.as<__nv_bfloat16>();
 
-  __nv_bfloat16 *vv = nullptr, *gate = nullptr;
-  CUtensorMap tm_vv, tm_gate, tm_yr, tm_vv_st, tm_gate_st, tm_u144;
-  if (toep) {
-    DevBuf& bvv = ctx->buf("act_vv");
-    DevBuf& bgt = ctx->buf("act_gate");
-    DCB_CHECK(bvv.reserve(T * kD * 2));
-    DCB_CHECK(bgt.reserve(T * kD * 2));
-    vv = bvv.as<__nv_bfloat16>();
-    gate = bgt.as<__nv_bfloat16>();
+  CUtensorMap tm_vv, tm_gate, tm_yr, tm_vv_st, tm_gate_st, tm_u144, tm_u, tm_y, tm_g, tm_hA;
+  if (!fft) {
     DCB_CHECK(make_tmap_3d_rows(&tm_vv, vv, B, kD, L));
     DCB_CHECK(make_tmap_3d_rows(&tm_gate, gate, B, kD, L));
     DCB_CHECK(make_tmap_3d_rows(&tm_yr, y, B, kD, L));
-    DCB_CHECK(make_tmap_3d_chbox(&tm_vv_st, vv, B, kD, L));
-    DCB_CHECK(make_tmap_3d_chbox(&tm_gate_st, gate, B, kD, L));
-    DCB_CHECK(make_tmap_2d(&tm_u144, u, T, kD, 144));
   }
-  CUtensorMap tm_u, tm_y, tm_g, tm_hA, tm_hB;
+  DCB_CHECK(make_tmap_3d_chbox(&tm_vv_st, vv, B, kD, L));
+  DCB_CHECK(make_tmap_3d_chbox(&tm_gate_st, gate, B, kD, L));
+  DCB_CHECK(make_tmap_2d(&tm_u144, u, T, kD, 144));
   DCB_CHECK(make_tmap_2d_f32(&tm_hA, hA, T, kD));
-  DCB_CHECK(make_tmap_2d_f32(&tm_hB, hB, T, kD));
   DCB_CHECK(make_tmap_2d(&tm_u, u, T, kD, 128));
   DCB_CHECK(make_tmap_3d_cm(&tm_y, y, B, kD, L));
   DCB_CHECK(make_tmap_2d(&tm_g, g, T, kInner, 128));
+
+  auto trace_buf = [&](int kind, int layer, long long** out) -> int {
+    *out = nullptr;
+    if (ctx->trace_kind != kind || layer != 0) return DCB200_OK;
+    DevBuf& bt = ctx->buf("trace");
+    DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
+    DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
+    *out = bt.as<long long>();
+    return DCB200_OK;
+  };
 
   {
     int blocks = (int)((T + 7) / 8);
     const int cap = ctx->sm_count * 8 * 4;
     if (blocks > cap) blocks = cap;
     ProfScope prof(ctx, K_EMBED);
-    embed_ln_kernel<<<blocks, 256, 0, ctx->stream>>>(tok, w->emb, w->layer[0].ln1_g, w->layer[0].ln1_b, (int)T, hA, u);
+    embed_ln_kernel<<<blocks, 256, 0, ctx->stream>>>(tok, w->emb, (int)T, hA, u);
     DCB_LAUNCH_CHECK(ctx);
   }
   DCB_STAGE_DONE();
-  GemmParams gp;
-  memset(&gp, 0, sizeof(gp));
-  gp.T = (int)T;
-  gp.L = L;
-  gp.num_outer = (int)(T / 128);
-  const FftPlan plan = make_plan(N);
   for (int l = 0; l < kLayers; ++l) {
     LayerW& lw = w->layer[l];
-    GemmParams p = gp;
-    if (toep) {
+    {
       // in_proj + short conv + first gate in one kernel: z never exists
       InprojParams ip;
       ip.num_tiles = (int)(T / 128);
@@ -507,100 +474,43 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
       ip.b_in = lw.b_in;
       ip.short_w = lw.short_w;
       ip.short_b = lw.short_b;
-      ip.trace = nullptr;
-      if (l == 0 && getenv("DCB200_TRACE") && !strcmp(getenv("DCB200_TRACE"), "inproj")) {
-        DevBuf& bt = ctx->buf("trace");
-        DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
-        DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
-        ip.trace = bt.as<long long>();
-      }
+      DCB_CHECK(trace_buf(TRACE_INPROJ, l, &ip.trace));
       DCB_CHECK(launch_inproj_conv(ctx, tm_u144, lw.tm_in_mc, tm_vv_st, tm_gate_st, ip));
-      DCB_STAGE_DONE();
-      DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, w->toep_cap, tm_vv, tm_gate, tm_yr, B, L));
-    } else {
-      p.bias = lw.b_in;
-      p.out_bf16 = z;
-      DCB_CHECK(launch_gemm(ctx, G_INPROJ, lw.tm_in, tm_u, p));
-      DCB_STAGE_DONE();
-      ConvParams cp;
-      cp.z = z;
-      cp.y = y;
-      cp.short_w = lw.short_w;
-      cp.short_b = lw.short_b;
-      cp.KF = lw.KF[N];
-      cp.tw = w->tw[N];
-      cp.B = B;
-      cp.L = L;
-      cp.plan = plan;
-      DCB_CHECK(launch_fftconv(ctx, cp));
     }
     DCB_STAGE_DONE();
-
-    const char* blk = getenv("DCB200_BLOCK");
-    if (!(blk && !strcmp(blk, "split"))) {
+    if (fft) DCB_CHECK(launch_lconv(ctx, vv, gate, y, lw.lc_K, w->lc_nbK, w->lc_tw, B, L));
+    else DCB_CHECK(launch_toeplitz_conv(ctx, lw.toep, w->toep_cap, tm_vv, tm_gate, tm_yr, B, L));
+    DCB_STAGE_DONE();
+    {
       // out_proj + LN2 + MLP + residual + next LN in one kernel: h1 and m never leave the SM
       static thread_local BlockParams bp;  // 11 KB: keep it off the stack
       bp.num_pairs = (int)((T / 128 + 1) / 2);
       bp.T = (int)T;
       bp.L = L;
-      bp.trace = nullptr;
-      if (l == 0 && getenv("DCB200_TRACE") && !strcmp(getenv("DCB200_TRACE"), "block")) {
-        DevBuf& bt = ctx->buf("trace");
-        DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
-        DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
-        bp.trace = bt.as<long long>();
-      }
+      DCB_CHECK(trace_buf(TRACE_BLOCK, l, &bp.trace));
       memcpy(bp.bo, lw.hb_out.data(), sizeof(bp.bo));
       memcpy(bp.b1, lw.hb_fc1.data(), sizeof(bp.b1));
       memcpy(bp.b2, lw.hb_fc2.data(), sizeof(bp.b2));
-      // residual stream updated in place: h (hA) -> h (hA); every tile reads its rows before it writes them
+      // residual stream updated in place: every tile reads its rows before it writes them
       DCB_CHECK(launch_block(ctx, tm_y, lw.tm_wou, lw.tm_w1u, lw.tm_w2u, tm_hA, tm_hA, tm_u, bp));
-      DCB_STAGE_DONE();
-      DCB_STAGE_DONE();
-      DCB_STAGE_DONE();
-      continue;
     }
-    p = gp;
-    p.bias = lw.b_out;
-    p.resid = hA;
-    p.h_out = hB;
-    p.ln_g = lw.ln2_g;
-    p.ln_b = lw.ln2_b;
-    p.out_bf16 = u;
-    DCB_CHECK(launch_gemm(ctx, G_OUTPROJ, tm_y, lw.tm_out, p));
     DCB_STAGE_DONE();
-
-    {
-      static thread_local MlpParams mp;  // 7 KB: keep it off the stack
-      mp.num_pairs = (int)((T / 128 + 1) / 2);
-      mp.T = (int)T;
-      mp.h_in = hB;
-      mp.h_out = hA;
-      mp.u_out = u;
-      memcpy(mp.b1, lw.hb_fc1.data(), sizeof(mp.b1));
-      memcpy(mp.b2, lw.hb_fc2.data(), sizeof(mp.b2));
-      memcpy(mp.ln_g, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_g.data() : w->h_lnf_g.data(), sizeof(mp.ln_g));
-      memcpy(mp.ln_b, (l + 1 < kLayers) ? w->layer[l + 1].h_ln1_b.data() : w->h_lnf_b.data(), sizeof(mp.ln_b));
-      mp.trace = nullptr;
-      if (l == 0 && getenv("DCB200_TRACE") && !strcmp(getenv("DCB200_TRACE"), "mlp")) {
-        DevBuf& bt = ctx->buf("trace");
-        DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
-        DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));
-        mp.trace = bt.as<long long>();
-      }
-      DCB_CHECK(launch_mlp(ctx, tm_u, lw.tm_w1u, lw.tm_w2u, tm_hB, tm_hA, tm_u, mp));
-      DCB_STAGE_DONE();
-      DCB_STAGE_DONE();
-    }
+    DCB_STAGE_DONE();
+    DCB_STAGE_DONE();
   }
-  GemmParams p = gp;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = (int)T;
+  p.L = L;
+  p.num_outer = (int)(T / 128);
   p.bias = w->bh1;
   p.qual = qual;
   p.out_bf16 = g;
   DCB_CHECK(launch_gemm(ctx, G_HEAD1, tm_u, w->tm_h1, p));
   DCB_STAGE_DONE();
-  p = gp;
   p.bias = w->bh2;
+  p.qual = nullptr;
+  p.out_bf16 = nullptr;
   p.r_in = g;
   p.w3 = w->w3;
   p.b3 = w->b3;

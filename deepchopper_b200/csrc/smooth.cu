@@ -165,6 +165,33 @@ __device__ __forceinline__ uint32_t load_word(const SmoothArgs& a, int64_t g0, b
   return r;
 }
 
+// The int8 path's word load split in two so that the 32 bytes can be in flight while other work runs: issue() starts the
+// two 16-byte loads (or resolves a word at the edge of the buffer byte by byte), word() packs them.
+struct RawWord {
+  uint4 v0, v1;
+  uint32_t slow;
+  bool fast;
+};
+__device__ __forceinline__ RawWord issue_word(const SmoothArgs& a, int64_t g0, bool wanted) {
+  RawWord r;
+  r.fast = false;
+  r.slow = 0;
+  r.v0 = r.v1 = make_uint4(0u, 0u, 0u, 0u);
+  if (!wanted || g0 >= a.total || g0 + 32 <= 0) return r;
+  if (g0 >= 0 && g0 + 32 <= a.total) {
+    const uint4* q = reinterpret_cast<const uint4*>(a.labels + g0);  // g0 chosen so the address is 32B aligned
+    r.v0 = __ldg(q);
+    r.v1 = __ldg(q + 1);
+    r.fast = true;
+    return r;
+  }
+  for (int i = 0; i < 32; ++i) r.slow |= label_at<false>(a, g0 + i) << i;
+  return r;
+}
+__device__ __forceinline__ uint32_t finish_word(const RawWord& r) {
+  return r.fast ? (pack16(r.v0) | (pack16(r.v1) << 16)) : r.slow;
+}
+
 __device__ __forceinline__ uint32_t mask_below(int64_t n, int64_t word) {  // bits of word with position < n
   int64_t lo = word * 32;
   if (lo + 32 <= n) return 0xffffffffu;
@@ -190,9 +217,53 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
   const int W = 2 * h + 1;
   const int approved = a.p.approved_interval_number;
 
+  // Software pipeline across reads (int8 labels): while read r is processed, the first 1 KB of read r + nwarps is already
+  // in flight and the (start, length) of read r + 2 nwarps is being fetched -- a warp's dependent chain
+  // metadata -> labels -> votes -> coordinates would otherwise leave one 1 KB load per warp in flight.
+  int64_t start_n = 0, n_n = 0, start_nn = 0, n_nn = 0;
+  RawWord pre;
+  pre.fast = false;
+  pre.slow = 0;
+  pre.v0 = pre.v1 = make_uint4(0u, 0u, 0u, 0u);
+  auto plan_read = [&](int64_t st, int64_t nn, int& mis_o, int64_t& abase_o) -> bool {  // false: nothing to load
+    mis_o = 0;
+    abase_o = st;
+    if (!LOGITS) {
+      mis_o = (int)((reinterpret_cast<uintptr_t>(a.labels) + (uintptr_t)st) & 31);
+      abase_o = st - mis_o;
+    }
+    return nn > 0 && ((a.smoothed != nullptr) || nn >= a.p.min_read_length);
+  };
+  if (warp_global < a.R) {
+    start_n = a.starts[warp_global];
+    n_n = a.lens[warp_global];
+    if (!LOGITS) {
+      int mis0;
+      int64_t ab0;
+      const bool live = plan_read(start_n, n_n, mis0, ab0);
+      pre = issue_word(a, ab0 + 32 * (int64_t)lane, live && lane <= n_n / 32 + 1);
+    }
+    if (warp_global + nwarps < a.R) {
+      start_nn = a.starts[warp_global + nwarps];
+      n_nn = a.lens[warp_global + nwarps];
+    }
+  }
   for (int64_t r = warp_global; r < a.R; r += nwarps) {
-    const int64_t start = a.starts[r];
-    const int64_t n = a.lens[r];
+    const int64_t start = start_n;
+    const int64_t n = n_n;
+    const RawWord cur = pre;
+    start_n = start_nn;
+    n_n = n_nn;
+    if (!LOGITS && r + nwarps < a.R) {
+      int mis1;
+      int64_t ab1;
+      const bool live = plan_read(start_n, n_n, mis1, ab1);
+      pre = issue_word(a, ab1 + 32 * (int64_t)lane, live && lane <= n_n / 32 + 1);
+    }
+    if (r + 2 * nwarps < a.R) {
+      start_nn = a.starts[r + 2 * nwarps];
+      n_nn = a.lens[r + 2 * nwarps];
+    }
     int total = 0;
     const bool skip = (!a.smoothed) && (n < a.p.min_read_length);  // src/bin/predict.rs:146-148
     if (n > 0 && !skip) {
@@ -206,14 +277,13 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
       const int64_t NW = n / 32 + 1;  // words 0..n/32 cover positions 0..n (position n closes a trailing run)
       const int64_t nchunks = (NW + 31) / 32;
 
-      // right-edge window (i + h + 1 > n): [max(0,n-W), n), identical for all such positions
+      // right-edge window (i + h + 1 > n): [max(0,n-W), n), identical for all such positions; its count of ones is
+      // taken from the packed words of the chunk(s) that hold right-edge positions (no extra byte loads)
       const int sizeR = (int)(n < W ? n : W);
       int cR = 0;
-      for (int t = lane; t < sizeR; t += 32) cR += label_at<LOGITS>(a, start + n - sizeR + t);
-      cR = __reduce_add_sync(0xffffffffu, cR);
       const int64_t redge = n - h > 0 ? n - h : 0;  // first right-edge position
 
-      uint32_t A0 = load_word<LOGITS>(a, abase + 32 * (int64_t)lane, lane <= NW);
+      uint32_t A0 = LOGITS ? load_word<LOGITS>(a, abase + 32 * (int64_t)lane, lane <= NW) : finish_word(cur);
       uint32_t prev_word = 0;      // raw word k-1 for lane 0
       uint32_t prev_S_last = 0;    // smoothed bit of position 32k-1 for lane 0
       int open_start = -1;         // most recent run start seen in earlier chunks
@@ -253,6 +323,13 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
           if (lane == 0) S = (S & ~lmask) | (lbits & lmask);
         }
         // right edge: positions >= max(0, n-h) share one window
+        if (h > 0 && 1024 * (c + 1) > redge) {  // (warp-uniform) this chunk holds right-edge positions
+          const int64_t lo_pos = n - sizeR;     // window = [lo_pos, n): at most 21 bits, within words 32c-1 .. 32(c+1)
+          int cnt = __popc(w & ~mask_below(lo_pos, k));
+          if (lane == 0 && c > 0) cnt += __popc(wprev & ~mask_below(lo_pos, k - 1));
+          if (lane == 31) cnt += __popc(wn0 & ~mask_below(lo_pos, k + 1));
+          cR = __reduce_add_sync(0xffffffffu, cnt);
+        }
         {
           const int64_t lo = 32 * k;
           if (lo + 32 > redge && h > 0) {

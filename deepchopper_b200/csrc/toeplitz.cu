@@ -1,4 +1,5 @@
-// Tensor-core form of the Hyena long convolution for L <= 4096:
+// Tensor-core form of the Hyena long convolution, the product path below the crossover with the blocked FFT kernel
+// (lconv.cu; any L <= 32768 works):
 //   y[b,c,t] = gate[b,c,t] * sum_{s<=t} vv[b,c,s] * k'_c[t-s],   vv = sc(v) * sc(x1),  gate = sc(x0),  k'[0] = k[0] + D
 //
 // Per channel the causal convolution is a GEMM  Y[b, t] = sum_s V[b, s] K[s, t]  with a Toeplitz K.  One CTA owns a
@@ -25,9 +26,6 @@
 #include "gemm.h"
 #include "ptx.cuh"
 #include "toeplitz.h"
-
-#include <stdlib.h>
-#include <string.h>
 
 namespace dcb {
 
@@ -359,10 +357,8 @@ int launch_toeplitz_conv(dcb200_ctx* ctx, const __nv_bfloat16* E, int cap, const
   const size_t want = (size_t)kTzAStages * kTzStage + (size_t)kTzGSlots * kTzBox + 1024 + 512;
   p.trace = nullptr;
   {
-    const char* te = getenv("DCB200_TRACE");
-    static thread_local bool traced_once = false;
-    if (te && !strcmp(te, "toeplitz") && !traced_once) {
-      traced_once = true;
+    if (ctx->trace_kind == TRACE_TOEPLITZ && !ctx->traced_once) {
+      ctx->traced_once = true;
       DevBuf& bt = ctx->buf("trace");
       DCB_CHECK(bt.reserve(3 * 4096 * 2 * 8));
       DCB_CUDA(cudaMemsetAsync(bt.p, 0, 3 * 4096 * 2 * 8, ctx->stream));

@@ -154,15 +154,9 @@ def id_rows(index: FastqIndex, rows: Sequence[int], truncated: np.ndarray) -> np
 def encode_batch_device(bytes_dev, seq_off_dev, qual_off_dev, len_dev, Lpad: int, ctx=None, Lrow: int | None = None):
     """dcb200_encode_batch on torch CUDA tensors -> (tok uint8 [R,Lpad], qual float32 [R,Lpad])."""
     import torch
-    ctx = ctx or _native.torch_context(bytes_dev.device)
-    R = int(len_dev.numel())
+    from . import ops  # noqa: F401  (registers torch.ops.dcb200.*)
     Lrow = int(Lrow or (Lpad + 3) // 4 * 4)
-    tok = torch.empty((R, Lrow), dtype=torch.uint8, device=bytes_dev.device)
-    qual = torch.empty((R, Lrow), dtype=torch.float32, device=bytes_dev.device)
-    check(lib().dcb200_encode_batch(ctx.handle, C.c_void_p(bytes_dev.data_ptr()), C.c_void_p(seq_off_dev.data_ptr()),
-                                    C.c_void_p(qual_off_dev.data_ptr()), C.c_void_p(len_dev.data_ptr()), R, int(Lpad), Lrow,
-                                    C.c_void_p(tok.data_ptr()), C.c_void_p(qual.data_ptr())))
-    return tok, qual
+    return torch.ops.dcb200.encode(bytes_dev, seq_off_dev, qual_off_dev, len_dev, int(Lpad), Lrow)
 
 
 def encode_records(recs: Sequence[Tuple[str, str, str]], Lpad: int, device="cuda"):

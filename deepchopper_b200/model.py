@@ -2,7 +2,7 @@
 returning a module with ``forward(input_ids, input_quals) -> logits[B,L,2]`` and Lightning-style
 ``predict_step(batch, idx) -> (logits, batch["labels"])`` (deepchopper/models/basic_module.py:90-100,197-207).
 
-The arithmetic runs in libdcb200 (tcgen05 GEMMs, smem FFT long conv, fused head) -- bf16 operands,
+The arithmetic runs in libdcb200 (tcgen05 GEMMs, Toeplitz / blocked-FFT long conv, fused head) -- bf16 operands,
 fp32 accumulation, fp32 residual stream.  CUDA only; there is no CPU path.
 """
 from __future__ import annotations
@@ -43,6 +43,8 @@ class Weights:
         self.ctx = ctx
         check(lib().dcb200_weights_create(ctx.handle, arr_names, arr_ptrs, arr_numel, n, C.byref(self._h)))
         del keep
+        from . import ops
+        self.op_handle = ops.register_weights(self)   # what torch.ops.dcb200.forward takes
 
     @property
     def handle(self):
@@ -50,6 +52,8 @@ class Weights:
 
     def close(self):
         if self._h:
+            from . import ops
+            ops.unregister_weights(self.op_handle)
             lib().dcb200_weights_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -103,14 +107,8 @@ class DeepChopperModel(torch.nn.Module):
         B, L = tok.shape
         assert L % ROW_TILE == 0 and tok.dtype == torch.uint8 and quals.dtype == torch.float32
         assert tok.is_contiguous() and quals.is_contiguous()
-        logits = torch.empty((B, L, 2), dtype=torch.float32, device=tok.device) if want_logits else None
-        labels = torch.empty((B, L), dtype=torch.uint8, device=tok.device) if want_labels else None
-        ctx = self._ctx_now()
-        check(lib().dcb200_forward(ctx.handle, self._weights.handle, C.c_void_p(tok.data_ptr()),
-                                   C.c_void_p(quals.data_ptr()), B, L,
-                                   C.c_void_p(logits.data_ptr()) if want_logits else None,
-                                   C.c_void_p(labels.data_ptr()) if want_labels else None))
-        return logits, labels
+        logits, labels = torch.ops.dcb200.forward(tok, quals, self._weights.op_handle, bool(want_logits), bool(want_labels))
+        return (logits if want_logits else None), (labels if want_labels else None)
 
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, input_quals: torch.Tensor) -> torch.Tensor:
@@ -134,6 +132,10 @@ class DeepChopperModel(torch.nn.Module):
 
     def eval(self):
         return self
+
+    def close(self):
+        """Release the device weights now (otherwise when the module is garbage-collected)."""
+        self._weights.close()
 
 
 class DeepChopper:

@@ -113,6 +113,23 @@ class DevicePipeline:
             self.items.append((b, so, qo, ln, st))
         torch.cuda.synchronize(dev)
 
+    def upload_items(self, items):
+        """``items`` = [(Batch, buf u8, seq_off, qual_off, len i32)] with offsets relative to each batch's own byte
+        buffer (what bench.py synthesises per batch): one device blob, offsets rebased."""
+        dev = self.device
+        total = int(sum(it[1].size for it in items))
+        self.blob = torch.empty(max(1, total), dtype=torch.uint8, device=dev)
+        self.items = []
+        base = 0
+        for b, buf, so, qo, ln in items:
+            self.blob[base:base + buf.size].copy_(torch.from_numpy(buf), non_blocking=False)
+            lens = ln.astype(np.int64)
+            st = torch.from_numpy(np.arange(b.rows.size, dtype=np.int64) * b.Lrow + (b.Lpad - 1) - lens).to(dev)
+            self.items.append((b, torch.from_numpy(so + base).to(dev), torch.from_numpy(qo + base).to(dev),
+                               torch.from_numpy(ln.astype(np.int32)).to(dev), st))
+            base += buf.size
+        torch.cuda.synchronize(dev)
+
     @torch.no_grad()
     def run_batch(self, item, want_logits=False):
         from .encode import encode_batch_device
@@ -164,6 +181,23 @@ class HostPipeline:
                         n_keep=np.zeros(R, np.int32), keep_iv=np.zeros((R, ap + 1, 2), np.int32),
                         action=np.zeros(R, np.uint8))
             self.items.append((b, buf, so, qo, ln.astype(np.int32), outs))
+
+    def pack_items(self, items, pin: bool = True):
+        """Adopt per-batch byte buffers that are already packed [sequences | quality strings] (see
+        DevicePipeline.upload_items): one pinned copy per batch."""
+        ap = int(self.params.approved_interval_number)
+        self.items = []
+        for b, nb, so, qo, ln in items:
+            buf = torch.empty(nb.size, dtype=torch.uint8)
+            if pin:
+                buf = buf.pin_memory()
+            buf.numpy()[:] = nb
+            R = b.rows.size
+            outs = dict(n_adapter=np.zeros(R, np.int32), adapter_iv=np.zeros((R, ap, 2), np.int32),
+                        n_keep=np.zeros(R, np.int32), keep_iv=np.zeros((R, ap + 1, 2), np.int32),
+                        action=np.zeros(R, np.uint8))
+            self.items.append((b, buf, np.ascontiguousarray(so, np.int64), np.ascontiguousarray(qo, np.int64),
+                               np.ascontiguousarray(ln, np.int32), outs))
 
     def bytes_per_pass(self):
         h2d = sum(it[1].numel() + it[2].nbytes + it[3].nbytes + it[4].nbytes + it[0].rows.size * 8 for it in self.items)

@@ -72,32 +72,14 @@ def smooth_chop_device(labels, starts, lens, params: Optional[ChopParams] = None
     ``logits=True``; starts int64 [R]; lens int32 [R]).  Returns torch tensors on the same device.
     Asynchronous on ``ctx``'s stream."""
     import torch
-    ctx = ctx or _native.torch_context(labels.device)
+    from . import ops
     p = params or ChopParams.default()
-    R = int(lens.numel())
-    ap = int(p.approved_interval_number)
-    dev = labels.device
-    n_ad = torch.zeros(R, dtype=torch.int32, device=dev)
-    ad = torch.zeros((R, ap, 2), dtype=torch.int32, device=dev)
-    n_keep = torch.zeros(R, dtype=torch.int32, device=dev)
-    keep = torch.zeros((R, ap + 1, 2), dtype=torch.int32, device=dev)
-    act = torch.zeros(R, dtype=torch.uint8, device=dev)
-    ql = None if qual_lens is None else C.c_void_p(qual_lens.data_ptr())
     if logits:
         assert labels.dtype == torch.float32 and labels.is_contiguous()
-        check(lib().dcb200_smooth_chop_logits(ctx.handle, C.c_void_p(labels.data_ptr()), labels.numel() // 2,
-                                              C.c_void_p(starts.data_ptr()), C.c_void_p(lens.data_ptr()), ql, R,
-                                              C.byref(p), C.c_void_p(n_ad.data_ptr()), C.c_void_p(ad.data_ptr()),
-                                              C.c_void_p(n_keep.data_ptr()), C.c_void_p(keep.data_ptr()),
-                                              C.c_void_p(act.data_ptr())))
     else:
         assert labels.dtype in (torch.int8, torch.uint8) and labels.is_contiguous()
-        check(lib().dcb200_smooth_chop(ctx.handle, C.c_void_p(labels.data_ptr()), labels.numel(),
-                                       C.c_void_p(starts.data_ptr()), C.c_void_p(lens.data_ptr()), ql, R, C.byref(p),
-                                       C.c_void_p(n_ad.data_ptr()), C.c_void_p(ad.data_ptr()),
-                                       C.c_void_p(n_keep.data_ptr()), C.c_void_p(keep.data_ptr()),
-                                       C.c_void_p(act.data_ptr())))
-    return n_ad, ad, n_keep, keep, act
+    ql = qual_lens if qual_lens is not None else torch.empty(0, dtype=torch.int32, device=labels.device)
+    return torch.ops.dcb200.smooth_chop(labels, starts, lens, ql, ops.params_list(p))
 
 
 def majority_voting_host(labels: np.ndarray, starts: np.ndarray, lens: np.ndarray, window: int,

@@ -92,6 +92,12 @@ int dcb200_ctx_sync(dcb200_ctx* ctx);
 void* dcb200_ctx_stream(dcb200_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t dcb200_ctx_launch_count(dcb200_ctx* ctx);
+/* ctx options.  "fft_min_len": reads (padded batch length) at least this long take the blocked shared-memory FFT
+ * long convolution (the reference's fftconv, SURVEY Appendix A / deepchopper/models/llm/hyena.py:34-41), shorter
+ * ones the tensor-core Toeplitz kernel; default = the measured crossover.  0 = always FFT, a huge value = never.
+ * dcb200_ctx_get_option returns -1 for an unknown name. */
+int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value);
+int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name);
 
 /* ---- FASTQ -> tokens + L2-normalised quality --------------------------------------------------
  * bytes: device-accessible FASTQ text (or any byte buffer holding seq and quality strings);
@@ -199,8 +205,8 @@ void dcb200_free(void* p);
  * dcb200_forward_debug == dcb200_forward that stops after `stop_stage` kernels of the forward chain
  * (0 embed+LN1, then per layer l: 1+5l in_proj, 2+5l conv, 3+5l out_proj, 4+5l fc1, 5+5l fc2; 21 head1,
  * 22 head2 = full).  dcb200_ctx_read_workspace copies a named internal activation buffer to the host:
- * "act_hA"/"act_hB" fp32 [T,256] residual stream, "act_u" bf16 [T,256], "act_z" bf16 [B,768,L],
- * "act_y" bf16 [B,256,L], "act_g" bf16 [T,1024].  Synchronises the stream. */
+ * "act_hA" fp32 [T,256] residual stream, "act_u" bf16 [T,256], "act_vv" / "act_gate" / "act_y" bf16 [B,256,L],
+ * "act_g" bf16 [T,1024].  Synchronises the stream. */
 int dcb200_forward_debug(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B,
                          int32_t L, float* logits, uint8_t* labels, int32_t stop_stage);
 int dcb200_ctx_read_workspace(dcb200_ctx* ctx, const char* name, void* host_dst, int64_t bytes);

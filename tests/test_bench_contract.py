@@ -30,3 +30,30 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0", "--ref-reads", "4"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_bench_global_job_is_rank_independent():
+    """bench.py --gpus N: ONE global job.  Lengths and batch plan are functions of the seed only; a batch's bytes are a
+    function of (seed, global batch index), so the read set does not depend on how many ranks share it; the shards of 1,
+    2 and 8 ranks partition the same batches and the token imbalance of the greedy deal stays small."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from deepchopper_b200.predict import plan_batches, shard_batches
+    lens = bench.synth_lengths(20000, 5, "configs1")
+    assert np.array_equal(lens, bench.synth_lengths(20000, 5, "configs1"))
+    batches = plan_batches(lens, token_budget=256 * 1024)
+    index_of = {id(b): i for i, b in enumerate(batches)}
+    all_tokens = sum(b.rows.size * b.Lrow for b in batches)
+    for world in (1, 2, 8):
+        shards = [shard_batches(batches, r, world) for r in range(world)]
+        assert sorted(index_of[id(b)] for s in shards for b in s) == list(range(len(batches)))
+        tok = [sum(b.rows.size * b.Lrow for b in s) for s in shards]
+        assert sum(tok) == all_tokens and max(tok) / (sum(tok) / world) < 1.1
+    b = batches[3]
+    items_a = bench.make_items(lens, [b], 5, index_of)
+    items_b = bench.make_items(lens, [batches[0], b], 5, index_of)
+    assert np.array_equal(items_a[0][1], items_b[1][1]) and np.array_equal(items_a[0][4], lens[b.rows].astype(np.int32))
+    buf, so, qo, ln = items_a[0][1:]
+    assert buf.size == 2 * int(ln.sum()) and set(np.unique(buf[: int(ln.sum())])) <= set(b"ACGTN")
+    assert buf[int(ln.sum()):].min() >= 34 and buf[int(ln.sum()):].max() <= 83 and qo[0] == int(ln.sum())

@@ -15,7 +15,27 @@ pytestmark = pytest.mark.gpu
 # stated near-tie positions"):
 LOGIT_ATOL_VS_FP32 = 5e-2     # |logit_gpu - logit_fp32_oracle|, bf16 operands / fp32 accumulate through 4 layers + head
 LOGIT_ATOL_VS_BF16EMU = 2e-2  # vs the oracle with bf16 rounding emulated at the same points
-NEAR_TIE = 1e-1               # positions with |l1 - l0| < NEAR_TIE in the fp32 oracle may flip
+# Positions with |l1 - l0| < NEAR_TIE in the fp32 oracle may flip.  The measured max |logit error| is 6e-3 per class
+# (so a margin can move by at most ~1.2e-2): NEAR_TIE is 2e-2, outside it every label must be identical, and the
+# overall flip fraction (near ties included) is bounded by MAX_FLIP_FRACTION.  With RANDOM-INIT weights the margins are
+# tiny (mean |logit| ~0.1, 6-12 % of all positions inside the 2e-2 band, ~4 % inside 8e-3), so 1-1.5 % of the labels
+# sit closer to the boundary than the bf16 error and flip; measured 0.2-1.5 % per batch (printed by every test).
+NEAR_TIE = 2e-2
+MAX_FLIP_FRACTION = 2.5e-2
+
+
+def check_labels(name, got, want):
+    """`got`, `want`: logits [..., 2].  Labels identical outside the near-tie band; flip fraction bounded and printed."""
+    lab_got = got[..., 1] > got[..., 0]
+    lab_want = want[..., 1] > want[..., 0]
+    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
+    flips = (lab_got != lab_want).float().mean().item()
+    exempt = 1.0 - decided.float().mean().item()
+    print(f"{name}: near-tie (exempt) fraction {exempt:.4f}, label flips overall {flips:.5f}, "
+          f"positive fraction {lab_want.float().mean().item():.3f}")
+    assert torch.equal(lab_got[decided], lab_want[decided]), f"{name}: a label outside the near-tie band differs"
+    assert flips <= MAX_FLIP_FRACTION, f"{name}: {flips:.4f} of the labels flipped"
+    return flips, exempt
 
 
 @pytest.fixture(scope="module")
@@ -77,11 +97,21 @@ def close(name, got, want, atol, rtol):
     assert worst <= 0, f"{name}: max err {err.max().item()} (|ref| mean {want.abs().mean().item()})"
 
 
+def set_conv(model, kind):
+    """Pick the long-convolution kernel for every length: block-Toeplitz tcgen05 GEMMs / blocked shared-memory FFT /
+    the product's own choice (crossover `fft_min_len`)."""
+    ctx = model._ctx_now()
+    if not hasattr(set_conv, "default"):
+        set_conv.default = ctx.get_option("fft_min_len")
+    ctx.set_option("fft_min_len", {"toeplitz": 1 << 30, "fft": 0, "auto": set_conv.default}[kind])
+
+
 @pytest.fixture(params=["toeplitz", "fft"])
-def conv_kind(request, monkeypatch):
-    """Both long-convolution kernels (block-Toeplitz tcgen05 GEMMs / shared-memory FFT) at the same sizes."""
-    monkeypatch.setenv("DCB200_CONV", request.param)
-    return request.param
+def conv_kind(request, gpu):
+    """Both long-convolution kernels at the same sizes."""
+    set_conv(gpu, request.param)
+    yield request.param
+    set_conv(gpu, "auto")
 
 
 @pytest.mark.parametrize("B,L", [(4, 256), (3, 384), (130, 640)])
@@ -104,18 +134,14 @@ def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
         # stage 1: in_proj (oracle op applied to the GPU's own bf16 input isolates the kernel)
         run_debug(gpu, tok, qd, 1)
         z_ref = F.linear(u, bf(lay.mixer.in_linear.weight), lay.mixer.in_linear.bias).transpose(1, 2)
-        if conv_kind == "fft":
-            z = read_ws(gpu, "act_z", (B, 768, L), "bf16")
-            close("in_proj", z, z_ref, 2e-2, 1e-2)
-        else:
-            # fused front end: in_proj + short conv + first gate; z stays on chip in fp32
-            z = z_ref
-            zc = lay.mixer.short_filter(z)[..., :L]
-            x0r, x1r, vr = zc.split(256, dim=1)
-            vv = read_ws(gpu, "act_vv", (B, 256, L), "bf16")
-            gate = read_ws(gpu, "act_gate", (B, 256, L), "bf16")
-            close("gate", gate, x0r, 1e-2, 1e-2)
-            close("vv", vv, vr * x1r, 1e-2, 1e-2)
+        # fused front end: in_proj + short conv + first gate; z stays on chip in fp32
+        z = z_ref
+        zc = lay.mixer.short_filter(z)[..., :L]
+        x0r, x1r, vr = zc.split(256, dim=1)
+        vv = read_ws(gpu, "act_vv", (B, 256, L), "bf16")
+        gate = read_ws(gpu, "act_gate", (B, 256, L), "bf16")
+        close("gate", gate, x0r, 1e-2, 1e-2)
+        close("vv", vv, vr * x1r, 1e-2, 1e-2)
         # stage 2: short conv + gate + long conv + gate
         run_debug(gpu, tok, qd, 2)
         y = read_ws(gpu, "act_y", (B, 256, L), "bf16")
@@ -125,6 +151,11 @@ def test_layer0_stage_by_stage(ref, gpu, B, L, conv_kind):
         y_ref = H.fftconv_ref(v * x1, k, lay.mixer.filter_fn.bias) * x0
         # bf16 activations in and out (and bf16 filter taps on the Toeplitz path): ~0.4 % of the local signal scale
         close("hyena_conv", y, y_ref, 3e-2 * y_ref.pow(2).mean().sqrt().item() + 1e-3, 2e-2)
+        # the long convolution alone, applied to the GPU's own bf16 inputs: the FFT kernel keeps the filter and every
+        # intermediate in fp32, so only the bf16 rounding of its output is left
+        y_own = H.fftconv_ref(vv, k, lay.mixer.filter_fn.bias) * gate
+        tol = (1e-2 if conv_kind == "toeplitz" else 1e-4) * y_own.pow(2).mean().sqrt().item()
+        close("long conv on the GPU's own vv / gate", y, y_own, tol, 8e-3)
         # stages 3-5: block tail in one kernel (out_proj + residual + LN2 + fc1 + gelu + fc2 + residual + next LN1);
         # h1, m and the hidden activation stay on chip, so the reference chain is applied to the GPU's own y
         run_debug(gpu, tok, qd, 5)
@@ -148,12 +179,7 @@ def test_forward_logits_and_labels(ref, gpu, B, L, conv_kind):
     got = gpu(ids.cuda(), q.cuda()).cpu()
     close("logits vs fp32 oracle", got, want, LOGIT_ATOL_VS_FP32, 0.0)
     close("logits vs bf16-emulating oracle", got, want_emu, LOGIT_ATOL_VS_BF16EMU, 0.0)
-    lab_got = got[..., 1] > got[..., 0]
-    lab_want = want[..., 1] > want[..., 0]
-    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
-    print(f"decided fraction {decided.float().mean().item():.4f}, flips overall {(lab_got != lab_want).float().mean().item():.5f}")
-    assert decided.float().mean() > 0.5
-    assert torch.equal(lab_got[decided], lab_want[decided])
+    check_labels(f"B={B} L={L}", got, want)
     # the u8 label output is exactly `logit1 > logit0` of the logits the same call returns
     tok = ids.to(torch.uint8).cuda()
     lg, lb = gpu.forward_tokens(tok, q.cuda(), True, True)
@@ -170,19 +196,23 @@ def test_forward_long_read(ref, gpu, B, L, conv_kind):
     close(f"logits L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
 
 
-@pytest.mark.parametrize("B,L", [(2, 12032), (1, 32768)])
-def test_forward_very_long_read(ref, gpu, B, L):
-    """BASELINE config 4 (16-32 kb reads): the Toeplitz long convolution covers the model's whole 32768-token range."""
-    rng = np.random.default_rng(13)
-    ids, q = make_batch(rng, B, L)
-    with torch.no_grad():
-        want = ref(ids, q)
-    got = gpu(ids.cuda(), q.cuda()).cpu()
-    close(f"logits L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
-    lab_got = got[..., 1] > got[..., 0]
-    lab_want = want[..., 1] > want[..., 0]
-    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
-    assert torch.equal(lab_got[decided], lab_want[decided])
+@pytest.mark.parametrize("B,L,kind", [(2, 12032, "auto"), (3, 16512, "auto"), (1, 32768, "auto"), (2, 24576, "auto"),
+                                      (2, 12032, "toeplitz"), (1, 32768, "toeplitz")])
+def test_forward_very_long_read(ref, gpu, B, L, kind):
+    """BASELINE configs[3] (16-32 kb reads): the product's choice above the crossover is the blocked FFT convolution
+    (2, 3 and 4 blocks of 8192 tokens here, odd row counts, a last block of 128 tokens); the Toeplitz kernel still
+    covers the model's whole 32768-token range."""
+    set_conv(gpu, kind)
+    try:
+        rng = np.random.default_rng(13)
+        ids, q = make_batch(rng, B, L)
+        with torch.no_grad():
+            want = ref(ids, q)
+        got = gpu(ids.cuda(), q.cuda()).cpu()
+    finally:
+        set_conv(gpu, "auto")
+    close(f"logits L={L} ({kind})", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    check_labels(f"L={L} ({kind})", got, want)
 
 
 def test_forward_arbitrary_length_is_right_filled(ref, gpu):
@@ -219,8 +249,7 @@ def test_forward_nontrivial_layernorm_affine():
             want = ref2(ids, q)
         got = gpu2(ids.cuda(), q.cuda()).cpu()
         close(f"logits (random LayerNorm affine) L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
-        decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
-        assert torch.equal((got[..., 1] > got[..., 0])[decided], (want[..., 1] > want[..., 0])[decided])
+        check_labels(f"random LayerNorm affine L={L}", got, want)
 
 
 @pytest.mark.parametrize("B,L", [(1, 128), (1, 256), (3, 128), (7, 384)])
@@ -233,5 +262,93 @@ def test_forward_tiny_batches(ref, gpu, B, L):
         want = ref(ids, q)
     got = gpu(ids.cuda(), q.cuda()).cpu()
     close(f"logits B={B} L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
-    decided = (want[..., 1] - want[..., 0]).abs() >= NEAR_TIE
-    assert torch.equal((got[..., 1] > got[..., 0])[decided], (want[..., 1] > want[..., 0])[decided])
+    check_labels(f"tiny B={B} L={L}", got, want)
+
+
+def test_forward_tokens_n_and_unk(ref, gpu):
+    """Token ids the other tests never feed: N (11) and UNK (6, what the tokenizer gives '-' and anything exotic), plus
+    the never-produced ids 0..3 / 5 / 12..15 of the padded 16-row embedding table."""
+    rng = np.random.default_rng(77)
+    B, L = 6, 640
+    ids, q = make_batch(rng, B, L)
+    for b in range(B):
+        pos = torch.from_numpy(rng.integers(0, L - 1, 60))
+        ids[b, pos[:25]] = 11
+        ids[b, pos[25:50]] = 6
+        ids[b, pos[50:]] = torch.from_numpy(rng.choice([0, 2, 3, 5, 12, 15], 10))
+    with torch.no_grad():
+        want = ref(ids, q)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    close("logits with N / UNK tokens", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+    check_labels("N / UNK tokens", got, want)
+
+
+def test_forward_benchmark_shape_sampled_rows(ref, gpu):
+    """One full-budget batch of the benchmarked shape (configs[1]: ~1 M padded tokens, 832 rows x 1280).  Rows are
+    independent (no attention mask, no cross-row op), so the fp32 oracle is run on 32 sampled rows of the same batch."""
+    rng = np.random.default_rng(2026)
+    B, L = 832, 1280
+    ids, q = make_batch(rng, B, L, min_len=1000)
+    got = gpu(ids.cuda(), q.cuda()).cpu()
+    rows = torch.from_numpy(np.sort(rng.choice(B, 32, replace=False)))
+    rows[0], rows[-1] = 0, B - 1
+    with torch.no_grad():
+        want = ref(ids[rows], q[rows])
+    close("logits, 32 sampled rows of an 832 x 1280 batch", got[rows], want, LOGIT_ATOL_VS_FP32, 0.0)
+    check_labels("832 x 1280 batch", got[rows], want)
+
+
+def trained_like_model(seed=3):
+    """Random-init weights have a narrow dynamic range.  A "trained-like" set: filter MLP and its sine frequencies scaled
+    up (sharper, larger filters), decay rates spread over 30x, large skip term, non-trivial LayerNorm affine parts."""
+    ref2 = H.make_reference_model(seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for name, prm in ref2.named_parameters():
+            if ".norm1." in name or ".norm2." in name or ".ln_f." in name:
+                if name.endswith("weight"):
+                    prm.copy_(0.5 + torch.rand(prm.shape, generator=g))
+                else:
+                    prm.copy_(0.3 * torch.randn(prm.shape, generator=g))
+            elif "implicit_filter.6.weight" in name:
+                prm.mul_(3.0)
+            elif "implicit_filter" in name and name.endswith("freq"):
+                prm.mul_(1.5)
+            elif "modulation.deltas" in name:
+                prm.mul_(torch.logspace(-1.0, 0.5, prm.shape[-1]).reshape(prm.shape))
+            elif "filter_fn.bias" in name:
+                prm.mul_(2.0)
+    return ref2
+
+
+@pytest.mark.parametrize("kind", ["toeplitz", "fft"])
+def test_forward_trained_like_weights_long(kind):
+    """L = 8192 with a wider dynamic range of the filter than random init gives (the Toeplitz kernel rounds the taps to
+    bf16, the reference keeps the convolution in fp32)."""
+    from deepchopper_b200.model import DeepChopper
+    ref2 = trained_like_model()
+    gpu2 = DeepChopper.from_state_dict(ref2.state_dict(), device=0)
+    set_conv(gpu2, kind)
+    try:
+        rng = np.random.default_rng(41)
+        for B, L in [(2, 8192), (4, 1536)]:
+            ids, q = make_batch(rng, B, L)
+            with torch.no_grad():
+                want = ref2(ids, q)
+            got = gpu2(ids.cuda(), q.cuda()).cpu()
+            close(f"logits (trained-like weights, {kind}) L={L}", got, want, LOGIT_ATOL_VS_FP32, 0.0)
+            check_labels(f"trained-like weights, {kind}, L={L}", got, want)
+    finally:
+        set_conv(gpu2, "auto")
+
+
+def test_fft_conv_matches_toeplitz_conv(gpu):
+    """The two long-convolution kernels on the same batch: logits agree to the bf16 tap rounding of the Toeplitz path."""
+    rng = np.random.default_rng(5)
+    ids, q = make_batch(rng, 3, 6144)
+    out = {}
+    for kind in ("toeplitz", "fft"):
+        set_conv(gpu, kind)
+        out[kind] = gpu(ids.cuda(), q.cuda()).cpu()
+    set_conv(gpu, "auto")
+    close("fft vs toeplitz logits", out["fft"], out["toeplitz"], 2e-2, 0.0)

@@ -22,3 +22,19 @@ for line in src:
         print("  roofline", d["roofline"])
     if "cpu_baseline" in d:
         print("  cpu_baseline", d["cpu_baseline"])
+    for name, ex in (d.get("extra_configs") or {}).items():
+        if "error" in ex:
+            print(f"  extra[{name}] ERROR {ex['error']}")
+            continue
+        r = ex.get("roofline") or {}
+        print(f"  extra[{name}] {ex['value']:.4g} {ex['unit']}  ms/step {ex['ms_per_step']:.2f}  roofline {r.get('kernel')} "
+              f"{r.get('bound')} frac {r.get('frac', 0):.3f}" + (f"  conv share {ex['conv_share']:.3f}" if "conv_share" in ex else "")
+              + (f"  e2e {ex['e2e']['value']:.4g}" if "e2e" in ex else ""))
+        for k, v in (ex.get("kernels") or {}).items():
+            print(f"      {k:16s} {v['ms_total']:9.2f} ms  share {v['share']:.3f}  {v.get('bound')} frac {v.get('frac') or 0:.3f}")
+        if ex.get("hyena_layer"):
+            print("      hyena_layer", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in ex["hyena_layer"].items() if k != "note"})
+    if "gpu_eager_baseline" in d:
+        print("  gpu_eager_baseline", d["gpu_eager_baseline"])
+    if "sharding" in d:
+        print("  sharding", d["sharding"])
