@@ -302,6 +302,16 @@ def gpu_eager_baseline(sd, seed: int, dev, n_reads: int = 1536):
 
 # ---- our arm -----------------------------------------------------------------------------------------
 
+def takes_fft(L: int, fft_min_len: int) -> bool:
+    """Mirror of model.cu:use_fft_conv (which long-convolution kernel a batch of padded length L takes)."""
+    if L < fft_min_len or L > 32768:
+        return False
+    if fft_min_len != 6144:
+        return True
+    nb = (L + 8191) // 8192
+    return nb * 8192.0 * (1.57, 1.76, 1.95, 2.06)[nb - 1] / L < 0.29e-3 * L
+
+
 def conv_work(batches, fft_min_len):
     """Which long-convolution kernel each batch takes (ctx option fft_min_len) -> per-step padded tokens of each kernel,
     the Toeplitz kernel's MMA FLOPs and the FFT kernel's fp32 FLOPs (5 N log2 N per complex transform of N = 8192
@@ -309,7 +319,7 @@ def conv_work(batches, fft_min_len):
     w = {"fft_tokens": 0, "toeplitz_tokens": 0, "toeplitz_flops": 0.0, "fft_flops": 0.0}
     for b in batches:
         t = b.rows.size * b.Lrow
-        if b.Lrow >= fft_min_len:
+        if takes_fft(b.Lrow, fft_min_len):
             w["fft_tokens"] += t
             blocks = (b.Lrow + 8191) // 8192
             w["fft_flops"] += b.rows.size * 256 * blocks * 2 * 5.0 * 8192 * 13

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdcb200.so")
+LIB_PATH = os.environ.get("DCB200_LIB") or os.path.join(_HERE, "lib", "libdcb200.so")   # (override: kernel experiments)
 
 EXPORTS = [
     "dcb200_last_error", "dcb200_version", "dcb200_chop_params_default", "dcb200_ctx_create", "dcb200_ctx_destroy",
@@ -16,6 +16,7 @@ EXPORTS = [
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
     "dcb200_kernel_kind_name", "dcb200_chop_write_bgzf",
     "dcb200_read_file_inflate", "dcb200_free", "dcb200_ctx_set_option", "dcb200_ctx_get_option",
+    "dcb200_index_fastq",
 ]
 
 
@@ -37,6 +38,12 @@ class ChopParams(C.Structure):
 class FastqIndexC(C.Structure):
     """dcb200_fastq_index."""
     _fields_ = [("fastq", C.c_void_p), ("name_off", C.c_void_p), ("name_len", C.c_void_p), ("head_len", C.c_void_p),
+                ("seq_off", C.c_void_p), ("seq_len", C.c_void_p), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p)]
+
+
+class FastqIndexArrays(C.Structure):
+    """dcb200_fastq_index_arrays (malloc'ed by dcb200_index_fastq)."""
+    _fields_ = [("n_records", C.c_int64), ("name_off", C.c_void_p), ("name_len", C.c_void_p), ("head_len", C.c_void_p),
                 ("seq_off", C.c_void_p), ("seq_len", C.c_void_p), ("qual_off", C.c_void_p), ("qual_len", C.c_void_p)]
 
 
@@ -82,6 +89,7 @@ def lib():
     l.dcb200_kernel_kind_name.restype = C.c_char_p
     pp = C.POINTER(ChopParams)
     l.dcb200_read_file_inflate.argtypes = [C.c_char_p, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32)]
+    l.dcb200_index_fastq.argtypes = [vp, i64, i32, C.POINTER(FastqIndexArrays)]
     l.dcb200_free.argtypes = [vp]
     l.dcb200_free.restype = None
     l.dcb200_chop_write_bgzf.argtypes = [C.POINTER(FastqIndexC), i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, C.c_char_p,

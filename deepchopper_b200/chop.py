@@ -148,8 +148,15 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
     n_pred_ids = set()
     pseq_fastq = None          # predicted sequence of compact batches = the normalised FASTQ sequence (ACGT, else N)
     n_batches = 0
+    t_index = time.time()
+    t_load = t_dev = 0.0
     # ---- predictions: GPU argmax + smooth + intervals + chop coordinates, one batch at a time ---------------
-    for d in it:
+    while True:
+        tl = time.time()
+        d = next(it, None)
+        t_load += time.time() - tl
+        if d is None:
+            break
         n_batches += 1
         if d.get("compact"):
             # compact sidecar: labels only; the sequence the reference decodes from the prediction tensor's tokens is a
@@ -176,10 +183,12 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
         if strict_ids and (rows < 0).any():
             raise KeyError(f"id not found: {ids[int(np.flatnonzero(rows < 0)[0])]}")      # src/cli.rs:95
         qual_lens = np.where(rows >= 0, ix.qual_len[np.maximum(rows, 0)], lens).astype(np.int32)
+        td = time.time()
         n_ad, ad, n_keep, keep, act = smooth_chop_device(
             dev_in, torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev), params,
             torch.from_numpy(qual_lens).to(dev), logits=is_logits)
         n_ad, ad, n_keep, keep, act = (t.cpu().numpy() for t in (n_ad, ad, n_keep, keep, act))
+        t_dev += time.time() - td
         del dev_in, d
         n_pred_ids.update(ids)
         sel = rows >= 0                        # a later batch overrides an earlier one, like the reference's HashMap
@@ -220,7 +229,8 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
         import resource
         rss = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
         print(f"chop: {n_batches} prediction batches, {len(n_pred_ids)} predictions, {R} FASTQ records -> {n_out} records, "
-              f"{n_text} text bytes; smooth/intervals {t_pred - t_start:.2f} s, write {time.time() - t_pred:.2f} s, "
+              f"{n_text} text bytes; read+index FASTQ {t_index - t_start:.2f} s, load predictions {t_load:.2f} s, GPU smooth / "
+              f"intervals {t_dev:.2f} s, host scatter {t_pred - t_index - t_load - t_dev:.2f} s, write {time.time() - t_pred:.2f} s, "
               f"peak RSS {rss:.0f} MB")
     return out, len(n_pred_ids), n_out
 

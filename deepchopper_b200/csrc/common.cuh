@@ -69,8 +69,8 @@ struct DevBuf {
 namespace dcb {
 enum KernelKind { K_ENCODE = 0, K_EMBED, K_INPROJ, K_CONV, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_SMOOTH, K_OTHER, K_SCONV, K_TOEP, K_MLP, K_BLOCK, K_NKINDS };
 enum TraceKind { TRACE_NONE = 0, TRACE_INPROJ, TRACE_BLOCK, TRACE_TOEPLITZ };
-// Reads at least this long take the blocked FFT long convolution (lconv.cu), shorter ones the tensor-core Toeplitz
-// kernel (toeplitz.cu); measured crossover, see profiles/r02_summary.md
+// Batches shorter than this never take the blocked FFT long convolution (lconv.cu); above it the measured cost model of
+// model.cu:use_fft_conv decides between it and the tensor-core Toeplitz kernel (toeplitz.cu)
 constexpr int kDefaultFftMinLen = 6144;
 struct ProfRec {
   int kind;

@@ -215,3 +215,146 @@ extern "C" int dcb200_read_file_inflate(const char* path, int32_t threads, uint8
   *out_len = (int64_t)total;
   return DCB200_OK;
 }
+
+// ---- record index ------------------------------------------------------------------------------------------------------
+// Record boundaries of a FASTQ text (4-line records), found on host threads: every thread counts the newlines of its
+// slice of the buffer (memchr), a prefix sum places the slices' lines, every thread writes its line starts, then records
+// are assembled and validated in parallel.  Semantics of the reference's reader (deepchopper/data/only_fq.py:21-85 via
+// pyfastx, noodles in src/output/writefq.rs): '\r' before '\n' is stripped, trailing empty lines are ignored, the id is
+// the header up to the first blank, sequence and quality must be non-empty and of equal length.
+extern "C" int dcb200_index_fastq(const uint8_t* fastq, int64_t n_bytes, int32_t threads, dcb200_fastq_index_arrays* out) {
+  using dcb::set_error;
+  if ((!fastq && n_bytes) || n_bytes < 0 || !out) {
+    set_error("dcb200_index_fastq: bad argument");
+    return DCB200_EINVAL;
+  }
+  memset(out, 0, sizeof(*out));
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if ((int64_t)nt > n_bytes / (1 << 20) + 1) nt = (int)(n_bytes / (1 << 20) + 1);
+  const size_t n = (size_t)n_bytes;
+  auto slice = [&](int t) { return n * (size_t)t / (size_t)nt; };
+  // 1. newlines per slice
+  std::vector<size_t> cnt(nt + 1, 0);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const uint8_t* p = fastq + slice(t);
+        const uint8_t* e = fastq + slice(t + 1);
+        size_t c = 0;
+        while (p < e) {
+          const void* q = memchr(p, '\n', (size_t)(e - p));
+          if (!q) break;
+          ++c;
+          p = static_cast<const uint8_t*>(q) + 1;
+        }
+        cnt[t + 1] = c;
+      });
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
+  size_t n_nl = cnt[nt];
+  const bool tail_line = n > 0 && fastq[n - 1] != '\n';  // last line without a trailing newline
+  size_t n_lines = n_nl + (tail_line ? 1 : 0);
+  // line_end[i] = offset of the '\n' (or n for the unterminated tail); line i starts at line_end[i-1] + 1
+  std::vector<int64_t> line_end(n_lines + 1);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const uint8_t* p = fastq + slice(t);
+        const uint8_t* e = fastq + slice(t + 1);
+        size_t i = cnt[t];
+        while (p < e) {
+          const void* q = memchr(p, '\n', (size_t)(e - p));
+          if (!q) break;
+          line_end[i++] = static_cast<const uint8_t*>(q) - fastq;
+          p = static_cast<const uint8_t*>(q) + 1;
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  if (tail_line) line_end[n_nl] = (int64_t)n;
+  auto lstart = [&](size_t i) -> int64_t { return i == 0 ? 0 : line_end[i - 1] + 1; };
+  auto lend = [&](size_t i) -> int64_t {  // exclusive, '\r' stripped
+    int64_t e = line_end[i];
+    if (e > lstart(i) && fastq[e - 1] == '\r') --e;
+    return e;
+  };
+  while (n_lines && lend(n_lines - 1) == lstart(n_lines - 1)) --n_lines;  // trailing empty lines
+  if (n_lines % 4 != 0) {
+    set_error("FASTQ has %zu lines, not a multiple of 4", n_lines);
+    return DCB200_EINVAL;
+  }
+  const size_t R = n_lines / 4;
+  out->n_records = (int64_t)R;
+  if (R == 0) return DCB200_OK;
+  auto alloc = [&](size_t bytes) { return malloc(bytes ? bytes : 1); };
+  out->name_off = static_cast<int64_t*>(alloc(R * 8));
+  out->name_len = static_cast<int32_t*>(alloc(R * 4));
+  out->head_len = static_cast<int32_t*>(alloc(R * 4));
+  out->seq_off = static_cast<int64_t*>(alloc(R * 8));
+  out->seq_len = static_cast<int32_t*>(alloc(R * 4));
+  out->qual_off = static_cast<int64_t*>(alloc(R * 8));
+  out->qual_len = static_cast<int32_t*>(alloc(R * 4));
+  auto release = [&] {
+    free(out->name_off); free(out->name_len); free(out->head_len); free(out->seq_off); free(out->seq_len);
+    free(out->qual_off); free(out->qual_len);
+    memset(out, 0, sizeof(*out));
+  };
+  if (!out->name_off || !out->name_len || !out->head_len || !out->seq_off || !out->seq_len || !out->qual_off || !out->qual_len) {
+    release();
+    set_error("dcb200_index_fastq: out of memory for %zu records", R);
+    return DCB200_ENOMEM;
+  }
+  // 3. records (first error by record number wins)
+  std::atomic<long long> bad_rec(-1);
+  std::atomic<int> bad_kind(0);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const size_t r0 = R * (size_t)t / (size_t)nt, r1 = R * (size_t)(t + 1) / (size_t)nt;
+        for (size_t r = r0; r < r1; ++r) {
+          const int64_t hs = lstart(4 * r), he = lend(4 * r);
+          const int64_t ss = lstart(4 * r + 1), se = lend(4 * r + 1);
+          const int64_t ps = lstart(4 * r + 2);
+          const int64_t qs = lstart(4 * r + 3), qe = lend(4 * r + 3);
+          int kind = 0;
+          if (he <= hs || fastq[hs] != '@') kind = 1;
+          else if (lend(4 * r + 2) <= ps || fastq[ps] != '+') kind = 2;
+          else if (se - ss != qe - qs) kind = 3;
+          else if (se == ss) kind = 4;
+          if (kind) {
+            long long cur = bad_rec.load();
+            while ((cur < 0 || (long long)r < cur) && !bad_rec.compare_exchange_weak(cur, (long long)r)) {}
+            if (bad_rec.load() == (long long)r) bad_kind.store(kind);
+            continue;
+          }
+          out->name_off[r] = hs + 1;
+          out->head_len[r] = (int32_t)(he - hs - 1);
+          int64_t b = hs + 1;
+          while (b < he && fastq[b] != ' ' && fastq[b] != '\t') ++b;
+          out->name_len[r] = (int32_t)(b - hs - 1);
+          out->seq_off[r] = ss;
+          out->seq_len[r] = (int32_t)(se - ss);
+          out->qual_off[r] = qs;
+          out->qual_len[r] = (int32_t)(qe - qs);
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  if (bad_rec.load() >= 0) {
+    const long long r = bad_rec.load();
+    switch (bad_kind.load()) {
+      case 1: set_error("FASTQ record does not start with '@' (record %lld)", r); break;
+      case 2: set_error("FASTQ separator line does not start with '+' (record %lld)", r); break;
+      case 3: set_error("record %lld: sequence and quality lengths differ", r); break;
+      default: set_error("empty sequence in FASTQ (record %lld)", r); break;
+    }
+    release();
+    return DCB200_EINVAL;
+  }
+  return DCB200_OK;
+}

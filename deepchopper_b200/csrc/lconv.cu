@@ -77,7 +77,9 @@ struct LconvParams {
   int B, L, nb, nbK;
 };
 
-__global__ void __launch_bounds__(kThreads, 3) lconv_kernel(const LconvParams p) {
+// Two CTAs per SM (128 registers, no spills): measured 15-20 % faster than three CTAs at 80 registers with the twiddle
+// arrays spilling to local memory.
+__global__ void __launch_bounds__(kThreads, 2) lconv_kernel(const LconvParams p) {
   extern __shared__ float2 lconv_smem[];
   float2* X = lconv_smem;
   const int tid = threadIdx.x;
@@ -135,6 +137,14 @@ __global__ void __launch_bounds__(kThreads, 3) lconv_kernel(const LconvParams p)
       }
       __syncthreads();  // the next block's pass 0 overwrites the array
     }
+  }
+  // The scratch is dead now: drop its lines from L2 instead of writing them back.  (Measured: raising the persisting-L2
+  // set-aside for the evict_last lines makes this kernel 10 % faster and in_proj / block 50 % slower -- the carve-out is
+  // device-wide -- so the set-aside stays at its default and the policies are only hints.)
+  if (p.nb > 1) {
+    const char* sb = reinterpret_cast<const char*>(S);
+    for (int ofs = tid * 128; ofs < (p.nb - 1) * kSlots * (int)sizeof(float4); ofs += kThreads * 128)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(sb + ofs) : "memory");
   }
 }
 

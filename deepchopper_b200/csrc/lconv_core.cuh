@@ -45,19 +45,22 @@ constexpr int kTwT1 = 0, kTwT2 = kH, kTwT3 = 2 * kH, kTwTotal = 3 * kH;
 LC_HD int padi(int i) { return i + (i >> 4); }
 LC_HD int rev3(int p) { return ((p & 0xF) << 8) | (p & 0xF0) | ((p >> 8) & 0xF); }
 
+// Complex arithmetic (scalar fp32; measured: Blackwell's packed FADD2 / FMUL2 / FFMA2 forms shorten the instruction
+// stream by a quarter but not the run time -- the fp32 pipes, not the issue slots, are what the passes fill).
 LC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 LC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 LC_HD float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
 LC_HD float2 cmulc(float2 a, float2 b) {  // a * conj(b)
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
-LC_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 LC_HD float2 cfma(float2 a, float2 b, float2 c) {  // a * b + c
   return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y)));
 }
+LC_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-// Global accesses with an L2 eviction policy (createpolicy, lconv.cu): the per-CTA scratch of block spectra and the
-// filter spectra are re-read and should stay in L2 (evict_last), the activations stream through once (evict_first).
+// Global accesses with an L2 eviction policy (createpolicy, lconv.cu): the per-CTA scratch of block spectra is re-read
+// by the later blocks of the same sequence and should stay in L2 (evict_last), the activations stream through once
+// (evict_first); the filter spectra take the default policy (shared by the rows in flight, then dead).
 // `pol` is ignored by the host emulation.
 LC_HD float4 ld_f4_hint(const float4* p, uint64_t pol) {
 #if defined(__CUDA_ARCH__)
@@ -230,7 +233,9 @@ template <int PASS, bool INV> LC_HD void radix16_pass(float2* X, float2 w1, floa
   float2* Xb = X + padi(blk * n + j);
   float2 w[16];
   if (s > 1) twiddle_powers(w, w1, w4);
-#pragma unroll
+  // (not unrolled: the two halves run the same code, and the kernel's instruction footprint matters -- the CTAs of an SM
+  // are in different phases and share its instruction cache)
+#pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     float2* Xh = Xb + half * (kH + kH / 16);
     float2 a[16];
@@ -363,7 +368,7 @@ LC_HD void pointwise_group(float2* X, const float2* __restrict__ T3, const float
     const int slot = (it0 + g) * kThreads + tid;
     slot_positions(slot, pa[g], pb[g], special[g]);
     w[g] = T3[slot];
-    k0[g] = ld_f4_hint(K + slot, pol_keep);
+    k0[g] = K[slot];
   }
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -394,7 +399,7 @@ LC_HD void pointwise_group(float2* X, const float2* __restrict__ T3, const float
     for (int g = 0; g < G; ++g) {
       const int slot = (it0 + g) * kThreads + tid;
       sj[g] = ld_f4_hint(S + (size_t)j * kSlots + slot, pol_keep);
-      kd[g] = ld_f4_hint(K + (size_t)(i - j) * kSlots + slot, pol_keep);
+      kd[g] = K[(size_t)(i - j) * kSlots + slot];
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {

@@ -393,6 +393,21 @@ static int ensure_lconv(dcb200_ctx* ctx, dcb200_weights* w, int L) {
   return DCB200_OK;
 }
 
+// Which long-convolution kernel a batch of padded length L takes.  Measured on B200 (profiles/r02_summary.md, 128 rows):
+// the Toeplitz kernel costs ~0.29 ns per token and layer per 1024 tokens of L (its MMA work grows with L); the FFT kernel
+// costs a fixed time per 8192-token block -- 1.57 / 1.76 / 1.95 / 2.06 ns per token slot for reads of 1 / 2 / 3 / 4 blocks
+// -- whether the last block is full or not.  So the FFT wins from ~6.7 k tokens up to 8192, loses again while a second
+// block is mostly empty (8.3 k - 9.9 k) and wins everywhere above.  An explicit "fft_min_len" option is a plain threshold.
+static bool use_fft_conv(const dcb200_ctx* ctx, int L) {
+  if (L < ctx->fft_min_len || L > lconv_max_len()) return false;
+  if (ctx->fft_min_len != kDefaultFftMinLen) return true;
+  static const double kSlotNs[4] = {1.57, 1.76, 1.95, 2.06};
+  const int nb = lconv_blocks_for(L);
+  const double fft_ns = nb * 8192.0 * kSlotNs[nb - 1] / L;
+  const double toeplitz_ns = 0.29e-3 * L;
+  return fft_ns < toeplitz_ns;
+}
+
 int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
                    float* logits, uint8_t* labels, int stop_stage) {
   int stage = 0;
@@ -406,9 +421,9 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     return DCB200_EINVAL;
   }
   // Long convolution: tensor-core Toeplitz GEMMs (MMA work grows with L) below the measured crossover, the blocked
-  // shared-memory FFT (O(L log L), fp32) above it.  ctx option "fft_min_len" moves the crossover (the tests run both
+  // shared-memory FFT (O(L log L), fp32) above it (use_fft_conv).  ctx option "fft_min_len" overrides (the tests run both
   // kernels at the same sizes).
-  const bool fft = L >= ctx->fft_min_len;
+  const bool fft = use_fft_conv(ctx, L);
   if (fft) DCB_CHECK(ensure_lconv(ctx, w, L));
   else DCB_CHECK(ensure_toeplitz(ctx, w, L));
   const size_t T = (size_t)B * L;

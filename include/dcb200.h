@@ -201,6 +201,25 @@ int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, const uint8_
 int dcb200_read_file_inflate(const char* path, int32_t threads, uint8_t** out, int64_t* out_len, int32_t* kind);
 void dcb200_free(void* p);
 
+/* Record index of a FASTQ text held in memory (4-line records), built on `threads` host threads (<= 0: all cores):
+ * replaces the per-record Python loop of deepchopper/data/only_fq.py:21-85 (pyfastx iteration + validation: '@' / '+'
+ * lines, equal and non-zero sequence / quality lengths) and the record splitting of noodles in src/output/writefq.rs.
+ * The id (name) is the header up to the first blank; '\r' before '\n' is stripped; trailing empty lines are ignored.
+ * The seven arrays are malloc'ed ([n_records] each) and released one by one with dcb200_free; on error nothing is
+ * allocated and dcb200_last_error() names the first offending record.  The result feeds dcb200_encode_batch /
+ * dcb200_predict_batch_host (seq_off, qual_off, len) and dcb200_chop_write_bgzf (dcb200_fastq_index). */
+typedef struct dcb200_fastq_index_arrays {
+  int64_t n_records;
+  int64_t* name_off;
+  int32_t* name_len;
+  int32_t* head_len;
+  int64_t* seq_off;
+  int32_t* seq_len;
+  int64_t* qual_off;
+  int32_t* qual_len;
+} dcb200_fastq_index_arrays;
+int dcb200_index_fastq(const uint8_t* fastq, int64_t n_bytes, int32_t threads, dcb200_fastq_index_arrays* out);
+
 /* ---- diagnostics (used by the parity tests to localise a mismatch) ---------------------------------
  * dcb200_forward_debug == dcb200_forward that stops after `stop_stage` kernels of the forward chain
  * (0 embed+LN1, then per layer l: 1+5l in_proj, 2+5l conv, 3+5l out_proj, 4+5l fc1, 5+5l fc2; 21 head1,

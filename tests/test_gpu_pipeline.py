@@ -151,3 +151,123 @@ def test_host_pipeline_equals_device_pipeline():
         assert np.array_equal(labels_d.cpu().numpy()[:, :b.Lpad], labels_h)
         assert np.array_equal(o["n_adapter"], n_ad.cpu().numpy()) and np.array_equal(o["action"], act.cpu().numpy())
         assert np.array_equal(o["adapter_iv"], ad.cpu().numpy()) and np.array_equal(o["keep_iv"], keep.cpu().numpy())
+
+
+def _write_fastq(tmp_path, recs, name="reads.fq"):
+    p = tmp_path / name
+    p.write_bytes(synth.fastq_text(recs))
+    return p
+
+
+def test_fused_predict_chop_equals_two_step(tmp_path):
+    """`predict --chop` (no prediction files) writes the same bytes as `predict --compact` + `chop` on the same batches."""
+    from deepchopper_b200 import cli
+    rng = np.random.default_rng(17)
+    lens = np.concatenate([synth.read_lengths(rng, 400, hi=4000), rng.integers(20, 150, 12)])
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    recs[5] = (recs[5][0] + " a description", recs[5][1], recs[5][2])
+    fq = _write_fastq(tmp_path, recs)
+    common = ["--random-init", "--bucket", "--token-budget", "65536"]
+    cli.main(["predict", str(fq), "-o", str(tmp_path / "pred"), "--compact"] + common)
+    cli.main(["chop", str(tmp_path / "pred" / "0"), str(fq), "-o", str(tmp_path / "two"), "-t", "4"])
+    cli.main(["predict", str(fq), "--chop", "--chop-output", str(tmp_path / "one"), "-t", "4"] + common)
+    two = [f for f in os.listdir(tmp_path) if f.startswith("two.")]
+    one = [f for f in os.listdir(tmp_path) if f.startswith("one.")]
+    assert len(two) == 1 and len(one) == 1 and two[0][3:] == one[0][3:]      # same {n}pd.{m}record counts
+    a = gzip.open(tmp_path / two[0], "rb").read()
+    b = gzip.open(tmp_path / one[0], "rb").read()
+    assert a == b and len(a) > 0
+
+
+def test_truncated_read_passes_through(tmp_path):
+    """A read of >= 32768 bases is cut to the model's window and flagged (tokenizer.py:154-163); `chop` then refuses to
+    cut it (prediction length != FASTQ quality length, src/bin/predict.rs:160-164) and emits the record verbatim.  The
+    `.pt` batch equals the oracle's tokenisation, the logits the fp32 oracle's, both routes write the oracle's bytes."""
+    from deepchopper_b200 import cli
+    from deepchopper_b200.chop import chop_fastq
+    from deepchopper_b200.init_weights import random_state_dict
+    rng = np.random.default_rng(23)
+    lens = np.array([700, 33000, 32768, 32767, 900])
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    fq = _write_fastq(tmp_path, recs)
+    out = tmp_path / "predictions"
+    cli.main(["predict", str(fq), "-o", str(out), "--random-init", "-b", "5", "--gpus", "1"])
+    d = torch.load(out / "0" / "0_0.pt")
+    feats = [H.tokenize_read(*r) for r in recs]
+    batch = H.collate(feats)
+    assert d["seq"].shape == (5, 32768) and torch.equal(d["seq"], batch["input_ids"])
+    assert torch.equal(d["id"], batch["id"].to(torch.int64)) and d["id"][:, 1].tolist() == [0, 1, 1, 0, 0]
+    assert torch.equal(d["target"], batch["labels"].to(torch.int64))
+    np.testing.assert_allclose(d["qual"].numpy(), batch["input_quals"].numpy(), rtol=1e-6, atol=1e-9)
+    ref = H.make_reference_model(0)
+    ref.load_state_dict(random_state_dict(0))
+    with torch.no_grad():
+        want = ref(batch["input_ids"], batch["input_quals"])
+    assert (d["prediction"] - want).abs().max() < 5e-2
+    o, npred, nrec = chop_fastq([str(out / "0")], str(fq), output_prefix=str(tmp_path / "y"))
+    want_txt, wp, wr = _oracle_text([d], recs, S.ChopOptions())
+    got = gzip.open(o, "rb").read().decode()
+    assert got == want_txt and (npred, nrec) == (wp, wr)
+    for k in (1, 2):   # the two truncated reads come out verbatim, whatever the labels say
+        rid, s, q = recs[k]
+        assert f"@{rid}\n{s}\n+\n{q}\n" in got
+    cli.main(["predict", str(fq), "--chop", "--chop-output", str(tmp_path / "z"), "--random-init", "-b", "5"])
+    z = [f for f in os.listdir(tmp_path) if f.startswith("z.")]
+    assert gzip.open(tmp_path / z[0], "rb").read().decode() == want_txt
+
+
+def test_predict_cli_and_loaders_on_gpu(tmp_path):
+    """The PyO3-named entry points: predict_cli (src/cli.rs:57-165) writes `.chop.fq.bgz` with the same records as the
+    chop driver; a prediction without a FASTQ record is an error there; Predict objects from load_predicts_from_batch_pts
+    smooth on the GPU like the oracle."""
+    import deepchopper_b200 as D
+    from deepchopper_b200 import writer
+    from deepchopper_b200.chop import chop_fastq
+    rng = np.random.default_rng(31)
+    lens = synth.read_lengths(rng, 60, hi=2500)
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    dicts = _planted_batches(recs, rng)
+    fq = _write_fastq(tmp_path, recs)
+    pdir = tmp_path / "predictions"
+    for i, d in enumerate(dicts):
+        writer.write_batch(str(pdir), 0, i, d)
+    D.predict_cli([str(pdir / "0")], str(fq), output_prefix=str(tmp_path / "pc"), threads=2)
+    o, npred, nrec = chop_fastq([str(pdir / "0")], str(fq), output_prefix=str(tmp_path / "cf"))
+    pc = [f for f in os.listdir(tmp_path) if f.startswith("pc.")]
+    assert pc == [f"pc.{npred}pd.{nrec}record.chop.fq.bgz"]                 # src/cli.rs:143-157
+    assert gzip.open(tmp_path / pc[0], "rb").read() == gzip.open(o, "rb").read()
+    fq2 = _write_fastq(tmp_path, recs[:-1], "fewer.fq")
+    with pytest.raises(KeyError, match="id not found"):
+        D.predict_cli([str(pdir / "0")], str(fq2), output_prefix=str(tmp_path / "bad"))
+    preds = D.load_predicts_from_batch_pts(str(pdir))
+    assert len(preds) == len(recs)
+    for rid in list(preds)[:10]:
+        p = preds[rid]
+        assert p.smooth_and_select_intervals(21, 13, 20) == [tuple(x) for x in S.smooth_label_region(p.prediction, 21, 13, 20)]
+        assert p.smooth_label(21) == S.majority_voting(p.prediction, 21)
+
+
+def test_torch_ops_direct():
+    """torch.ops.dcb200.* called directly: same results as the host mirror's functions; approved_interval_number = 0 is
+    legal (the reference then treats every read as having no interval -> passthrough)."""
+    import deepchopper_b200.ops as ops  # noqa: F401
+    from deepchopper_b200._native import ChopParams
+    from oracle import cref
+    rng = np.random.default_rng(2)
+    lens = synth.read_lengths(rng, 50, hi=1500)
+    lab, starts, ln = synth.planted_labels(rng, lens)
+    dev = torch.device("cuda", 0)
+    args = (torch.from_numpy(lab).to(dev), torch.from_numpy(starts).to(dev), torch.from_numpy(ln).to(dev),
+            torch.empty(0, dtype=torch.int32, device=dev))
+    p = ChopParams.default()
+    n_ad, ad, n_keep, keep, act = torch.ops.dcb200.smooth_chop(*args, ops.params_list(p))
+    chk = cref.load().smooth_chop(lab, starts, ln)
+    assert np.array_equal(n_ad.cpu().numpy(), chk["n_adapter"]) and np.array_equal(act.cpu().numpy(), chk["action"])
+    p0 = ChopParams.default(approved_interval_number=0)
+    n_ad0, ad0, n_keep0, keep0, act0 = torch.ops.dcb200.smooth_chop(*args, ops.params_list(p0))
+    assert ad0.shape == (50, 0, 2) and int(n_ad0.sum()) == 0 and int(act0.sum()) == 0
+    # logits form: fp32 [N, 2] -> argmax fused
+    lg = torch.zeros((lab.size, 2), device=dev)
+    lg[:, 1] = torch.from_numpy(lab.astype(np.float32)).to(dev) - 0.5
+    out2 = torch.ops.dcb200.smooth_chop(lg, *args[1:], ops.params_list(p))
+    assert torch.equal(out2[0], n_ad) and torch.equal(out2[4], act) and torch.equal(out2[1], ad)
