@@ -28,6 +28,11 @@ int weights_destroy(dcb200_weights* w);
 int forward_device(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
                    float* logits, uint8_t* labels, int stop_stage);
 
+__global__ void row_starts_kernel(const int32_t* __restrict__ len, int R, int Lrow, int Lpad, int64_t* __restrict__ starts) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) starts[r] = (int64_t)r * Lrow + (Lpad - 1 - len[r]);
+}
+
 static int check_params(const dcb200_chop_params* p) {
   DCB_ARG(p != nullptr);
   DCB_ARG(p->smooth_window_size >= 1 && p->smooth_window_size < (1 << 20));
@@ -366,16 +371,17 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   DCB_CHECK(stage_in(ctx, "p_qual_off", qual_off, (size_t)R * 8, &d_qo));
   DCB_CHECK(stage_in(ctx, "p_len", len, (size_t)R * 4, &d_len));
   if (qual_lens) DCB_CHECK(stage_in(ctx, "p_qlens", qual_lens, (size_t)R * 4, &d_ql));
-  // label-row starts: read r occupies columns [Lpad-len-1, Lpad-1) of row r (left pad, SEP last)
-  std::vector<int64_t> st(R);
+  // a bad offset from across the plain-pointer ABI must not become an out-of-bounds device read
   DCB_ARG((int64_t)R * Lrow <= INT_MAX / 2);
   for (int r = 0; r < R; ++r) {
     DCB_ARG(len[r] >= 0 && len[r] + 1 <= Lpad);
-    // a bad offset from across the plain-pointer ABI must not become an out-of-bounds device read
     DCB_ARG(seq_off[r] >= 0 && seq_off[r] + len[r] <= n_bytes && qual_off[r] >= 0 && qual_off[r] + len[r] <= n_bytes);
-    st[r] = (int64_t)r * Lrow + (Lpad - 1 - len[r]);
   }
-  DCB_CHECK(stage_in(ctx, "p_starts", st.data(), (size_t)R * 8, &d_st));
+  // label-row starts: read r occupies columns [Lpad-len-1, Lpad-1) of row r (left pad, SEP last); computed on the device
+  // from the lengths that are uploaded anyway (no host staging vector, no extra synchronisation)
+  DCB_CHECK(stage_out(ctx, "p_starts", (size_t)R * 8, &d_st));
+  row_starts_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>((const int32_t*)d_len, R, Lrow, Lpad, (int64_t*)d_st);
+  DCB_LAUNCH_CHECK(ctx);
   DCB_CHECK(stage_out(ctx, "p_tok", T, &d_tok));
   DCB_CHECK(stage_out(ctx, "p_qual", T * 4, &d_q));
   DCB_CHECK(stage_out(ctx, "p_labels", T, &d_lab));
@@ -385,8 +391,6 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   DCB_CHECK(stage_out(ctx, "h_nk", (size_t)R * 4, &d_nk));
   DCB_CHECK(stage_out(ctx, "h_kp", (size_t)R * (ap + 1) * 8, &d_kp));
   DCB_CHECK(stage_out(ctx, "h_act", (size_t)R, &d_act));
-  // the std::vector above must outlive its async copy
-  DCB_CUDA(cudaStreamSynchronize(ctx->stream));
   DCB_CUDA(cudaMemsetAsync(d_ad, 0, (size_t)R * ap * 8, ctx->stream));
   DCB_CUDA(cudaMemsetAsync(d_kp, 0, (size_t)R * (ap + 1) * 8, ctx->stream));
   DCB_CHECK(encode_device(ctx, (const uint8_t*)d_bytes, (const int64_t*)d_so, (const int64_t*)d_qo, (const int32_t*)d_len, R,
