@@ -52,6 +52,8 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
         batches = plan_batches(lens, token_budget=token_budget)
     else:
         batches = plan_batches(lens, token_budget=1 << 62, max_rows=int(batch_size), sort=False)
+    # largest batch first: the library's grow-only workspaces are sized once (a regrowth frees and reallocates GBs)
+    batches = sorted(batches, key=lambda b: -b.rows.size * b.Lrow)
     t_index = time.time()
     blob = torch.from_numpy(buf).to(dev)
     torch.cuda.synchronize(dev)
@@ -73,6 +75,11 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
         starts = torch.arange(b.rows.size, dtype=torch.int64, device=dev) * b.Lrow + (b.Lpad - 1) - ln.to(torch.int64)
         # a read cut to the model's window has qual_len != predicted length -> passthrough (src/bin/predict.rs:160-164)
         outs.append(smooth_chop_device(labels.view(-1), starts, ln, params, qlen_dev[rows]))
+    # host work that does not need the GPU's results runs while the batches above are still executing
+    pseq = normalised_sequence_bytes(ix.buf)
+    pseq_ptr = (np.uint64(pseq.ctypes.data) + ix.seq_off.astype(np.uint64)).astype(np.uint64)
+    pseq_len = np.zeros(R, np.int32)
+    pseq_len[:n] = lens
     approved = int(params.approved_interval_number)
     has_pred = np.zeros(R, np.uint8)
     action = np.zeros(R, np.uint8)
@@ -91,10 +98,6 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
             ad_all[order, :approved] = ad
         keep_all[order] = keep
     t_gpu = time.time()
-    pseq = normalised_sequence_bytes(ix.buf)
-    pseq_ptr = (np.uint64(pseq.ctypes.data) + ix.seq_off.astype(np.uint64)).astype(np.uint64)
-    pseq_len = np.zeros(R, np.int32)
-    pseq_len[:n] = lens
     if output_prefix:
         out_dir = os.path.dirname(output_prefix) or "."
         stem = output_prefix

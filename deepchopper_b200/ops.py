@@ -14,7 +14,11 @@ CURRENT torch stream:
   src/smooth/predict.rs:186-209); fp32 ``labels`` [N,2] are read as logits (argmax fused, src/smooth/predict.rs:275).
 
 ``DeepChopperModel.forward`` / ``forward_tokens``, ``encode.encode_batch_device`` and ``smooth.smooth_chop_device`` call
-these ops, so the module is traceable as ordinary torch ops (fake / meta implementations are registered).
+these ops, so the module is traceable as ordinary torch ops (Meta implementations give the output shapes).
+
+The ops are defined with the low-level ``torch.library.Library`` API (schema + CUDA / Meta kernels): the
+``torch.library.custom_op`` decorator costs 2.7 s on the first call of a process (it pulls in the fake-tensor / FX stack),
+which is more than a 100k-read ``predict --chop`` run spends on the GPU.
 """
 from __future__ import annotations
 
@@ -47,7 +51,13 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-@torch.library.custom_op("dcb200::encode", mutates_args=(), device_types="cuda")
+_LIB = torch.library.Library("dcb200", "DEF")
+_LIB.define("encode(Tensor blob, Tensor seq_off, Tensor qual_off, Tensor lens, int Lpad, int Lrow) -> (Tensor, Tensor)")
+_LIB.define("forward(Tensor tok, Tensor qual, int weights, bool want_logits, bool want_labels) -> (Tensor, Tensor)")
+_LIB.define("smooth_chop(Tensor labels, Tensor starts, Tensor lens, Tensor qual_lens, int[] params) -> "
+            "(Tensor, Tensor, Tensor, Tensor, Tensor)")
+
+
 def encode(blob: torch.Tensor, seq_off: torch.Tensor, qual_off: torch.Tensor, lens: torch.Tensor, Lpad: int,
            Lrow: int) -> Tuple[torch.Tensor, torch.Tensor]:
     assert blob.dtype == torch.uint8 and seq_off.dtype == torch.int64 and qual_off.dtype == torch.int64
@@ -61,13 +71,11 @@ def encode(blob: torch.Tensor, seq_off: torch.Tensor, qual_off: torch.Tensor, le
     return tok, qual
 
 
-@encode.register_fake
-def _(blob, seq_off, qual_off, lens, Lpad, Lrow):
+def _encode_meta(blob, seq_off, qual_off, lens, Lpad, Lrow):
     R = lens.numel()
     return blob.new_empty((R, Lrow), dtype=torch.uint8), blob.new_empty((R, Lrow), dtype=torch.float32)
 
 
-@torch.library.custom_op("dcb200::forward", mutates_args=(), device_types="cuda")
 def forward(tok: torch.Tensor, qual: torch.Tensor, weights: int, want_logits: bool,
             want_labels: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     B, L = tok.shape
@@ -83,14 +91,12 @@ def forward(tok: torch.Tensor, qual: torch.Tensor, weights: int, want_logits: bo
     return logits, labels
 
 
-@forward.register_fake
-def _(tok, qual, weights, want_logits, want_labels):
+def _forward_meta(tok, qual, weights, want_logits, want_labels):
     B, L = tok.shape
     return (tok.new_empty((B, L, 2) if want_logits else (0, 0, 2), dtype=torch.float32),
             tok.new_empty((B, L) if want_labels else (0, 0), dtype=torch.uint8))
 
 
-@torch.library.custom_op("dcb200::smooth_chop", mutates_args=(), device_types="cuda")
 def smooth_chop(labels: torch.Tensor, starts: torch.Tensor, lens: torch.Tensor, qual_lens: torch.Tensor,
                 params: List[int]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """``qual_lens``: int32 [R], or an EMPTY tensor for "not given"; ``params``: the 8 fields of dcb200_chop_params."""
@@ -117,13 +123,18 @@ def smooth_chop(labels: torch.Tensor, starts: torch.Tensor, lens: torch.Tensor, 
     return n_ad, ad, n_keep, keep, act
 
 
-@smooth_chop.register_fake
-def _(labels, starts, lens, qual_lens, params):
+def _smooth_chop_meta(labels, starts, lens, qual_lens, params):
     R = lens.numel()
     ap = int(params[2])
     i32 = dict(dtype=torch.int32)
     return (lens.new_empty(R, **i32), lens.new_empty((R, ap, 2), **i32),
             lens.new_empty(R, **i32), lens.new_empty((R, ap + 1, 2), **i32), lens.new_empty(R, dtype=torch.uint8))
+
+
+for _name, _cuda, _meta in (("encode", encode, _encode_meta), ("forward", forward, _forward_meta),
+                            ("smooth_chop", smooth_chop, _smooth_chop_meta)):
+    _LIB.impl(_name, _cuda, "CUDA")     # CUDA only: a CPU tensor finds no kernel (no fallback)
+    _LIB.impl(_name, _meta, "Meta")
 
 
 def params_list(p: ChopParams) -> List[int]:

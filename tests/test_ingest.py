@@ -57,7 +57,7 @@ def test_native_index_equals_numpy_restatement():
     descriptions, no trailing newline, trailing blank lines, 1 / 3 / all threads; the same inputs are rejected."""
     import pytest
     from deepchopper_b200 import synth
-    from tests.helpers_index import index_fastq_numpy
+    from helpers_index import index_fastq_numpy
     rng = np.random.default_rng(11)
     recs = synth.fastq_reads(rng, 3000, 1, 400)
     recs[3] = (recs[3][0] + " some description", recs[3][1], recs[3][2])

@@ -4,7 +4,9 @@ import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.test_gpu_parity_configs0 import compare_configs0  # noqa: E402
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_gpu_parity_configs0 import compare_configs0  # noqa: E402
 
 print(json.dumps(compare_configs0(int(sys.argv[1]) if len(sys.argv) > 1 else 1000)))
