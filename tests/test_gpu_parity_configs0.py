@@ -60,8 +60,9 @@ def test_configs0_own_labels_interval_agreement():
     res = compare_configs0(160)
     print(res)
     assert res["max_abs_logit_error"] < 5e-2
-    assert res["label_flip_fraction"] < 2.5e-2
-    # Random-init weights put ~10 % of all positions within 2e-2 of a tie, so raw labels are noise-like (about half ones)
-    # and the smoothed intervals are dense: a single flipped base near a window tie moves an interval edge.  The bound
-    # is therefore loose; the figure itself is the result (printed, and recorded for 1000 reads in profiles/).
-    assert res["reads_with_identical_smoothed_intervals"] >= 0.0
+    assert res["label_flip_fraction"] < 5e-3       # configs[0] batches: measured 2-3e-4
+    # Random-init weights put ~10 % of all positions within 2e-2 of a tie, so raw labels are noise-like and a single
+    # flipped base next to a window tie moves an interval edge.  Measured: 96.9 % of 160 reads, 95.2 % of 1000 reads
+    # (profiles/r02_summary.md) come out with identical intervals AND chop decision; the bound leaves room for the seed.
+    assert res["reads_with_identical_smoothed_intervals"] >= 0.85
+    assert res["reads_with_identical_intervals_and_action"] >= 0.85
