@@ -142,6 +142,19 @@ extern "C" int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, c
     set_error("dcb200_chop_write_bgzf: null argument");
     return DCB200_EINVAL;
   }
+  // the interval tables are only read for the actions that need them: check them up front instead of faulting mid-file
+  for (int64_t r = 0; r < R; ++r) {
+    if (!has_pred[r]) continue;
+    const uint8_t a = action[r];
+    if (a == DCB200_ACTION_ADAPTERS && (!n_adapter || !adapter_iv || adapter_stride <= 0)) {
+      set_error("dcb200_chop_write_bgzf: record %lld needs the adapter intervals (action ADAPTERS) but none were given", (long long)r);
+      return DCB200_EINVAL;
+    }
+    if ((a == DCB200_ACTION_CHOP_T || a == DCB200_ACTION_CHOP_I) && (!n_keep || !keep_iv || keep_stride <= 0)) {
+      set_error("dcb200_chop_write_bgzf: record %lld needs the kept intervals (action CHOP) but none were given", (long long)r);
+      return DCB200_EINVAL;
+    }
+  }
   if (level < 0 || level > 9) level = 6;
   int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
   T = std::max(1, std::min(T, 256));

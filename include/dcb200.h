@@ -105,7 +105,9 @@ int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name);
  * (already truncated to max_tokens-1 by the caller, tokenizer.py:154-163); Lpad >= max(len)+1 is the
  * collated batch length (the reference pads to the batch maximum); Lrow >= Lpad, Lrow % 4 == 0, is the
  * row stride of tok/qual.  Row r = [PAD(4) x (Lpad-len-1)][bases][SEP(1)][PAD x (Lrow-Lpad)], qual 0
- * at pads and SEP.  The left pads are what the reference feeds the model; the right filler only
+ * at pads and SEP.  (Device form: the caller guarantees seq_off[r] + len[r] and qual_off[r] + len[r] lie inside `bytes`;
+ * nothing outside [string, string + len) is read.  The host form dcb200_predict_batch_host checks every offset against
+ * n_bytes.)  The left pads are what the reference feeds the model; the right filler only
  * rounds the row up to the kernels' tile size -- the model is causal, so it cannot influence
  * columns < Lpad. */
 int dcb200_encode_batch(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
@@ -143,7 +145,9 @@ int dcb200_smooth_chop_logits(dcb200_ctx* ctx, const float* logits, int64_t n_to
                               int32_t* n_adapter, int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv,
                               uint8_t* action);
 
-/* majority_voting over R reads; out has the layout of labels (only read positions are written). */
+/* majority_voting over R reads; out has the layout of labels (only read positions are written).  Label domain: a
+ * position counts as 1 iff its byte equals 1, anything else as 0 (the reference votes over arbitrary label values; on
+ * this path labels are the argmax of two classes). */
 int dcb200_majority_voting(dcb200_ctx* ctx, const int8_t* labels, int64_t labels_bytes, const int64_t* starts,
                            const int32_t* lens, int64_t R, int32_t window, int8_t* out);
 
