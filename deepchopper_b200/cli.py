@@ -155,10 +155,26 @@ def cmd_predict(args):
         from .fused import predict_chop_fastq
         p = params_from_cli(args.smooth_window, args.min_interval_size, args.approved_intervals, args.max_process_intervals,
                             args.min_read_length, args.output_chopped, args.chop_type)
+        # the FASTQ is read, inflated and indexed (native code, GIL released) while CUDA and the weights come up
+        from . import encode
+        loaded = {}
+
+        def _load():
+            try:
+                buf = encode.read_fastq_bytes(args.data_path)
+                loaded["v"] = (buf, encode.index_fastq(buf))
+            except BaseException as e:  # noqa: BLE001
+                loaded["e"] = e
+
+        th = threading.Thread(target=_load)
+        th.start()
         model = _load_model(args, torch.device("cuda", 0))
+        th.join()
+        if "e" in loaded:
+            raise loaded["e"]
         out, npred, nrec = predict_chop_fastq(args.data_path, model, p, args.chop_output, args.token_budget,
                                               None if args.bucket else args.batch_size, args.threads,
-                                              args.compression_level, args.max_sample, args.verbose)
+                                              args.compression_level, args.max_sample, args.verbose, loaded["v"])
         print(f"Wrote {nrec} records to {out} ({npred} predictions)")
         return
     from . import encode

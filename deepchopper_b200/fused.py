@@ -35,16 +35,20 @@ def normalised_sequence_bytes(buf: np.ndarray) -> np.ndarray:
 @torch.no_grad()
 def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, output_prefix: Optional[str] = None,
                        token_budget: int = 1024 * 1024, batch_size: Optional[int] = None, threads: int = 0, level: int = 6,
-                       max_sample: Optional[int] = None, verbose: bool = False) -> Tuple[str, int, int]:
+                       max_sample: Optional[int] = None, verbose: bool = False, preloaded=None) -> Tuple[str, int, int]:
     """FASTQ -> ``{prefix|stem}.{n_pred}pd.{n_out}record.chop.fq.gz``.  ``batch_size`` = None: length-bucketed batches of
     ~``token_budget`` padded tokens; an integer: the reference's FASTQ-order batches of that many reads (left pads are
     semantic, so the two give different logits near ties -- like any change of batch size in the reference).
-    Returns (output path, #predictions, #records written)."""
+    ``preloaded`` = (bytes, FastqIndex) when the caller already read and indexed the file (the CLI does that on a thread
+    while CUDA and the weights come up).  Returns (output path, #predictions, #records written)."""
     t0 = time.time()
     params = params or ChopParams.default()
     dev = model.device
-    buf = read_fastq_bytes(fq)
-    ix = index_fastq(buf)
+    if preloaded is not None:
+        buf, ix = preloaded
+    else:
+        buf = read_fastq_bytes(fq)
+        ix = index_fastq(buf)
     R = len(ix)
     n = R if max_sample is None else min(R, int(max_sample))
     lens = np.minimum(ix.seq_len[:n].astype(np.int64), MAX_TOKENS - 1)       # tokenizer.py:154-163 (truncation)
