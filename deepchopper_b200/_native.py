@@ -16,7 +16,7 @@ EXPORTS = [
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
     "dcb200_kernel_kind_name", "dcb200_chop_write_bgzf",
     "dcb200_read_file_inflate", "dcb200_free", "dcb200_ctx_set_option", "dcb200_ctx_get_option",
-    "dcb200_index_fastq",
+    "dcb200_index_fastq", "dcb200_chop_write_bgzf_part",
 ]
 
 
@@ -94,6 +94,8 @@ def lib():
     l.dcb200_free.restype = None
     l.dcb200_chop_write_bgzf.argtypes = [C.POINTER(FastqIndexC), i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, C.c_char_p,
                                          i32, i32, vp, vp]
+    l.dcb200_chop_write_bgzf_part.argtypes = [C.POINTER(FastqIndexC), i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32,
+                                              C.c_char_p, i32, i32, i32, vp, vp]
     l.dcb200_smooth_chop.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_smooth_chop_logits.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_majority_voting.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]

@@ -20,9 +20,12 @@ from .smooth import CHOP_TYPES, MIN_READ_LEN, _ID_TABLE, smooth_chop_device
 from .writer import COMPACT_SUFFIX, IGNORE, list_batches, read_batch_compact
 
 
+WRITE_APPEND, WRITE_NO_EOF = 1, 2     # dcb200_chop_write_bgzf_part flags
+
+
 def write_chopped_fastq(path: str, ix: FastqIndex, has_pred: np.ndarray, pseq_ptr: np.ndarray, pseq_len: np.ndarray,
                         action: np.ndarray, n_adapter: np.ndarray, adapter_iv: np.ndarray, n_keep: np.ndarray,
-                        keep_iv: np.ndarray, threads: int = 0, level: int = 6) -> Tuple[int, int]:
+                        keep_iv: np.ndarray, threads: int = 0, level: int = 6, flags: int = 0) -> Tuple[int, int]:
     """dcb200_chop_write_bgzf: record assembly + BGZF on host threads (src/bin/predict.rs:266-364,
     src/output/split.rs:60-226, src/output/writefq.rs).  All per-record arrays are in FASTQ order; ``pseq_ptr`` holds the
     address of each record's predicted sequence bytes (kept alive by the caller).  Returns (#records, #text bytes)."""
@@ -40,10 +43,11 @@ def write_chopped_fastq(path: str, ix: FastqIndex, has_pred: np.ndarray, pseq_pt
     adapter_iv, keep_iv = c(adapter_iv, np.int32), c(keep_iv, np.int32)
     assert adapter_iv.ndim == 3 and keep_iv.ndim == 3 and adapter_iv.shape[0] == R and keep_iv.shape[0] == R
     nrec, ntext = C.c_int64(0), C.c_int64(0)
-    check(lib().dcb200_chop_write_bgzf(C.byref(cix), R, has_pred.ctypes.data, pseq_ptr.ctypes.data, pseq_len.ctypes.data,
-                                       action.ctypes.data, n_adapter.ctypes.data, adapter_iv.ctypes.data,
-                                       adapter_iv.shape[1], n_keep.ctypes.data, keep_iv.ctypes.data, keep_iv.shape[1],
-                                       os.fsencode(path), int(threads), int(level), C.byref(nrec), C.byref(ntext)))
+    check(lib().dcb200_chop_write_bgzf_part(C.byref(cix), R, has_pred.ctypes.data, pseq_ptr.ctypes.data,
+                                            pseq_len.ctypes.data, action.ctypes.data, n_adapter.ctypes.data,
+                                            adapter_iv.ctypes.data, adapter_iv.shape[1], n_keep.ctypes.data,
+                                            keep_iv.ctypes.data, keep_iv.shape[1], os.fsencode(path), int(threads),
+                                            int(level), int(flags), C.byref(nrec), C.byref(ntext)))
     return int(nrec.value), int(ntext.value)
 
 
@@ -118,13 +122,18 @@ def _decode_pt_batch(d) -> Tuple[np.ndarray, np.ndarray, List[str], np.ndarray, 
 def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None, output_prefix: Optional[str] = None,
                max_batch_size: Optional[int] = None, device: int = 0, batches=None, threads: int = 0,
                level: int = 6, suffix: str = "gz", verbose: bool = False,
-               strict_ids: bool = False) -> Tuple[str, int, int]:
+               strict_ids: bool = False, chunk_bytes: Optional[int] = None) -> Tuple[str, int, int]:
     """src/bin/predict.rs:197-384.  Returns (output path, #predictions, #records written).
 
     Prediction files are consumed one at a time (per read only the chop decision, its <= 20 intervals and one byte per
     base of predicted sequence survive a batch); the FASTQ text is held whole, like the id -> Predict map the reference
     holds whole (src/bin/predict.rs:222-235)."""
     import time
+    if chunk_bytes is None and batches is None and not strict_ids and os.path.getsize(fq) > (2 << 30):
+        chunk_bytes = 256 << 20                  # large inputs are streamed (peak memory = one piece + the decision tables)
+    if chunk_bytes:
+        return chop_fastq_streaming(predicts, fq, params, output_prefix, max_batch_size, device, threads, level, chunk_bytes,
+                                    suffix, verbose)
     t_start = time.time()
     params = params or ChopParams.default()
     dev = torch.device("cuda", device)
@@ -233,6 +242,142 @@ def chop_fastq(predicts: List[str], fq: str, params: Optional[ChopParams] = None
               f"intervals {t_dev:.2f} s, host scatter {t_pred - t_index - t_load - t_dev:.2f} s, write {time.time() - t_pred:.2f} s, "
               f"peak RSS {rss:.0f} MB")
     return out, len(n_pred_ids), n_out
+
+
+def iter_fastq_chunks(path: str, chunk_bytes: int = 256 << 20):
+    """Whole-record pieces of a FASTQ file (plain or gzip / bgzip), each about ``chunk_bytes`` of text: the streaming
+    reader of src/output/writefq.rs:174-193 / src/bin/predict.rs:275-316.  A piece ends after a line count that is a
+    multiple of 4 (records are 4 lines, like the record index assumes)."""
+    import gzip
+    with open(path, "rb") as probe:
+        magic = probe.read(2)
+    f = gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb")
+    carry = b""
+    lines_mod = 0            # lines of the current record already inside `carry`
+    try:
+        while True:
+            data = f.read(chunk_bytes)
+            if not data:
+                break
+            buf = np.frombuffer(carry + data, dtype=np.uint8)
+            nl = np.flatnonzero(buf == 10)
+            usable = (nl.size // 4) * 4
+            if usable == 0:
+                carry = buf.tobytes()
+                continue
+            cut = int(nl[usable - 1]) + 1
+            yield buf[:cut]
+            carry = buf[cut:].tobytes()
+    finally:
+        f.close()
+    if carry.strip():
+        yield np.frombuffer(carry, dtype=np.uint8)
+
+
+def chop_fastq_streaming(predicts: List[str], fq: str, params: Optional[ChopParams] = None,
+                         output_prefix: Optional[str] = None, max_batch_size: Optional[int] = None, device: int = 0,
+                         threads: int = 0, level: int = 6, chunk_bytes: int = 256 << 20, suffix: str = "gz",
+                         verbose: bool = False) -> Tuple[str, int, int]:
+    """``chop`` with the FASTQ streamed in pieces like src/bin/predict.rs:275-316: the predictions are reduced to per-read
+    decisions first (id -> row of compact tables, the reference's id -> Predict map), then every FASTQ piece is indexed,
+    matched by id and appended to the output.  Peak memory = the decision tables + one piece, not the file.  The
+    decompressed output equals :func:`chop_fastq`'s."""
+    import time
+    t_start = time.time()
+    params = params or ChopParams.default()
+    dev = torch.device("cuda", device)
+    approved = int(params.approved_interval_number)
+    row_of_id: Dict[str, int] = {}
+    tabs = {k: [] for k in ("action", "n_ad", "ad", "n_keep", "keep", "plen", "poff")}
+    letters_chunks: List[np.ndarray] = []          # predicted sequences of .pt batches (1 byte per base)
+    letters_base = 0
+    n_rows = 0
+    for d in iter_prediction_batches(predicts, max_batch_size):
+        if d.get("compact"):
+            ids, offs = d["ids"], d["offsets"]
+            lens = np.diff(offs).astype(np.int32)
+            starts = offs[:-1].astype(np.int64)
+            dev_in, is_logits = torch.from_numpy(d["labels"]).to(dev), False
+            poff = np.full(len(ids), -1, np.int64)           # sequence comes from the FASTQ piece itself
+        else:
+            starts, lens, ids, _trunc, letters, loff = _decode_pt_batch(d)
+            dev_in, is_logits = d["prediction"].float().contiguous().to(dev), True
+            letters_chunks.append(letters)
+            poff = letters_base + loff[:-1]
+            letters_base += int(letters.size)
+        # no FASTQ yet: the truncation gate (prediction length != quality length -> passthrough, src/bin/predict.rs:160-164)
+        # is applied per piece below, exactly where the reference applies it
+        n_ad, ad, n_keep, keep, act = (t.cpu().numpy() for t in smooth_chop_device(
+            dev_in, torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev), params, None, logits=is_logits))
+        del dev_in, d
+        for k, rid in enumerate(ids):                          # a later batch overrides an earlier one (HashMap insert)
+            row_of_id[rid] = n_rows + k
+        n_rows += len(ids)
+        for key, val in (("action", act), ("n_ad", n_ad), ("ad", ad), ("n_keep", n_keep), ("keep", keep), ("plen", lens),
+                         ("poff", poff)):
+            tabs[key].append(val)
+    cat = lambda key, shape, dt: (np.concatenate(tabs[key]) if tabs[key] else np.zeros(shape, dt))  # noqa: E731
+    action_p, n_ad_p, n_keep_p = cat("action", 0, np.uint8), cat("n_ad", 0, np.int32), cat("n_keep", 0, np.int32)
+    ad_p, keep_p = cat("ad", (0, approved, 2), np.int32), cat("keep", (0, approved + 1, 2), np.int32)
+    plen_p, poff_p = cat("plen", 0, np.int32), cat("poff", 0, np.int64)
+    letters_all = np.concatenate(letters_chunks) if letters_chunks else np.zeros(1, np.uint8)
+    del letters_chunks
+    t_pred = time.time()
+    if output_prefix:
+        out_dir = os.path.dirname(output_prefix) or "."
+        stem = output_prefix
+    else:
+        out_dir = os.getcwd()
+        stem = os.path.splitext(os.path.basename(fq))[0]
+    tmp = os.path.join(out_dir, f".deepchopper_temp_{os.getpid()}.fq.gz")
+    open(tmp, "wb").close()
+    table = np.full(256, ord("N"), dtype=np.uint8)
+    for a, b in zip(b"ACGTacgtUu", b"ACGTACGTTT"):
+        table[a] = b
+    n_out = n_text = n_fq = n_pieces = 0
+    for piece in iter_fastq_chunks(fq, chunk_bytes):
+        ix = index_fastq(piece)
+        R = len(ix)
+        n_fq += R
+        n_pieces += 1
+        rows = np.fromiter((row_of_id.get(ix.name(r), -1) for r in range(R)), dtype=np.int64, count=R)
+        has = rows >= 0
+        pr = np.maximum(rows, 0)
+        act = np.where(has, action_p[pr] if action_p.size else 0, 0).astype(np.uint8)
+        plen = np.where(has, plen_p[pr] if plen_p.size else 0, 0).astype(np.int32)
+        act[has & (plen != ix.qual_len)] = 0                       # truncated prediction -> passthrough
+        n_ad = np.where(has, n_ad_p[pr] if n_ad_p.size else 0, 0).astype(np.int32)
+        n_keep = np.where(has & (act != 0), n_keep_p[pr] if n_keep_p.size else 0, 0).astype(np.int32)
+        ad = ad_p[pr] if ad_p.shape[0] else np.zeros((R, approved, 2), np.int32)
+        keep = keep_p[pr] if keep_p.shape[0] else np.zeros((R, approved + 1, 2), np.int32)
+        if ad.shape[1] == 0:
+            ad = np.zeros((R, 1, 2), np.int32)
+        pseq_piece = np.ascontiguousarray(table[piece])
+        poff = poff_p[pr] if poff_p.size else np.full(R, -1, np.int64)
+        ptr = np.where(poff >= 0, np.uint64(letters_all.ctypes.data) + np.maximum(poff, 0).astype(np.uint64),
+                       np.uint64(pseq_piece.ctypes.data) + ix.seq_off.astype(np.uint64)).astype(np.uint64)
+        nr, nt = write_chopped_fastq(tmp, ix, has.astype(np.uint8), ptr, plen, act, n_ad, ad, n_keep, keep, threads=threads,
+                                     level=level, flags=WRITE_APPEND | WRITE_NO_EOF)
+        n_out += nr
+        n_text += nt
+    # the BGZF end-of-file block
+    z = np.zeros(0, np.uint8)
+    end_ix = FastqIndex(z, z.astype(np.int64), z.astype(np.int32), z.astype(np.int32), z.astype(np.int64), z.astype(np.int32),
+                        z.astype(np.int64), z.astype(np.int32))
+    write_chopped_fastq(tmp, end_ix, z, z.astype(np.uint64), z.astype(np.int32), z, z.astype(np.int32),
+                        np.zeros((0, 1, 2), np.int32), z.astype(np.int32), np.zeros((0, approved + 1, 2), np.int32),
+                        threads=1, level=level, flags=WRITE_APPEND)
+    out = f"{stem}.{len(row_of_id)}pd.{n_out}record.chop.fq.{suffix}"
+    if not output_prefix and not os.path.isabs(out):
+        out = os.path.join(os.getcwd(), out)
+    os.replace(tmp, out)
+    if verbose:
+        import resource
+        rss = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
+        print(f"chop (streaming): {len(row_of_id)} predictions, {n_fq} FASTQ records in {n_pieces} pieces -> {n_out} records, "
+              f"{n_text} text bytes; predictions {t_pred - t_start:.2f} s, FASTQ pass {time.time() - t_pred:.2f} s, "
+              f"peak RSS {rss:.0f} MB")
+    return out, len(row_of_id), n_out
 
 
 # ---- PyO3-named entry points (src/python.rs:879-958) ---------------------------------------------------------

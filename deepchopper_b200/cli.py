@@ -199,7 +199,8 @@ def cmd_chop(args):
     p = params_from_cli(args.smooth_window, args.min_interval_size, args.approved_intervals, args.max_process_intervals,
                         args.min_read_length, args.output_chopped, args.chop_type)
     out, npred, nrec = chop_fastq(args.predicts, args.fq, p, args.output, args.max_batch, threads=args.threads,
-                                  level=args.compression_level, verbose=args.verbose)
+                                  level=args.compression_level, verbose=args.verbose,
+                                  chunk_bytes=(args.chunk_mb << 20) if args.chunk_mb else None)
     print(f"Wrote {nrec} records to {out} ({npred} predictions)")
 
 
@@ -252,6 +253,9 @@ def build_parser():
     ch.add_argument("fq")
     _add_chop_flags(ch, "--output -o")
     ch.add_argument("--max-batch", type=int, default=None)
+    ch.add_argument("--chunk-mb", type=int, default=0,
+                    help="stream the FASTQ in pieces of this many MB of text (src/bin/predict.rs:275-316 streams 10 000 "
+                         "records at a time); default: whole file below 2 GB, 256 MB pieces above")
     ch.add_argument("--verbose", "-v", action="store_true")     # cli.py:155-198 / src/bin/predict.rs:76-77
     ch.set_defaults(fn=cmd_chop)
     return ap

@@ -137,8 +137,18 @@ extern "C" int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, c
                                       const int32_t* n_adapter, const int32_t* adapter_iv, int32_t adapter_stride,
                                       const int32_t* n_keep, const int32_t* keep_iv, int32_t keep_stride, const char* path,
                                       int32_t threads, int32_t level, int64_t* n_records, int64_t* n_text_bytes) {
+  return dcb200_chop_write_bgzf_part(ix, R, has_pred, pseq, pseq_len, action, n_adapter, adapter_iv, adapter_stride, n_keep,
+                                     keep_iv, keep_stride, path, threads, level, 0, n_records, n_text_bytes);
+}
+
+extern "C" int dcb200_chop_write_bgzf_part(const dcb200_fastq_index* ix, int64_t R, const uint8_t* has_pred,
+                                           const uint8_t* const* pseq, const int32_t* pseq_len, const uint8_t* action,
+                                           const int32_t* n_adapter, const int32_t* adapter_iv, int32_t adapter_stride,
+                                           const int32_t* n_keep, const int32_t* keep_iv, int32_t keep_stride,
+                                           const char* path, int32_t threads, int32_t level, int32_t flags,
+                                           int64_t* n_records, int64_t* n_text_bytes) {
   using dcb::set_error;
-  if (!ix || !ix->fastq || R < 0 || !path || !has_pred || !action || (R > 0 && (!pseq || !pseq_len))) {
+  if (!ix || (!ix->fastq && R > 0) || R < 0 || !path || (R > 0 && (!has_pred || !action || !pseq || !pseq_len))) {
     set_error("dcb200_chop_write_bgzf: null argument");
     return DCB200_EINVAL;
   }
@@ -158,7 +168,7 @@ extern "C" int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, c
   if (level < 0 || level > 9) level = 6;
   int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
   T = std::max(1, std::min(T, 256));
-  FILE* f = fopen(path, "wb");
+  FILE* f = fopen(path, (flags & DCB200_WRITE_APPEND) ? "ab" : "wb");
   if (!f) {
     set_error("dcb200_chop_write_bgzf: cannot open '%s' for writing", path);
     return DCB200_EINVAL;
@@ -255,7 +265,7 @@ extern "C" int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, c
     total_text += w.text_bytes;
     w.done();
   }
-  if (rc == DCB200_OK && fwrite(kEof, 1, sizeof(kEof), f) != sizeof(kEof)) {
+  if (rc == DCB200_OK && !(flags & DCB200_WRITE_NO_EOF) && fwrite(kEof, 1, sizeof(kEof), f) != sizeof(kEof)) {
     set_error("dcb200_chop_write_bgzf: short write to '%s'", path);
     rc = DCB200_EINVAL;
   }

@@ -196,6 +196,18 @@ int dcb200_chop_write_bgzf(const dcb200_fastq_index* ix, int64_t R, const uint8_
                            const int32_t* n_keep, const int32_t* keep_iv, int32_t keep_stride, const char* path,
                            int32_t threads, int32_t level, int64_t* n_records, int64_t* n_text_bytes);
 
+/* The same for one CHUNK of records of a FASTQ that is streamed (src/bin/predict.rs:275-316 walks the FASTQ in chunks of
+ * 10 000 records): DCB200_WRITE_APPEND appends to `path` instead of truncating it, DCB200_WRITE_NO_EOF leaves out the
+ * 28-byte BGZF end-of-file block (every call but the last).  BGZF members concatenate, so the parts form one valid file
+ * whose decompressed bytes equal the one-call output.  R = 0 with neither flag writes an empty BGZF file. */
+#define DCB200_WRITE_APPEND 1
+#define DCB200_WRITE_NO_EOF 2
+int dcb200_chop_write_bgzf_part(const dcb200_fastq_index* ix, int64_t R, const uint8_t* has_pred,
+                                const uint8_t* const* pseq, const int32_t* pseq_len, const uint8_t* action,
+                                const int32_t* n_adapter, const int32_t* adapter_iv, int32_t adapter_stride,
+                                const int32_t* n_keep, const int32_t* keep_iv, int32_t keep_stride, const char* path,
+                                int32_t threads, int32_t level, int32_t flags, int64_t* n_records, int64_t* n_text_bytes);
+
 /* ---- FASTQ ingest, file level: plain / gzip / BGZF file -> one host buffer ----------------------------
  * Replaces the compression sniffing and single-threaded readers of src/output/writefq.rs:84-193 and the file access
  * of deepchopper/data/only_fq.py:21-85 (pyfastx).  BGZF blocks (bgzip, and what dcb200_chop_write_bgzf writes) are

@@ -114,3 +114,44 @@ def test_writer_rejects_unknown_action(tmp_path):
     act[2] = 9
     with pytest.raises(Dcb200Error):
         write_chopped_fastq(str(tmp_path / "bad.fq.gz"), ix, has, ptr, plen, act, n_ad, ad, n_keep, keep, threads=2)
+
+
+def test_writer_parts_append_to_one_valid_file(tmp_path):
+    """dcb200_chop_write_bgzf_part: the records written in three appended parts (the last one closing the file with the
+    BGZF end-of-file block) decompress to the one-call output, and the file is still a well-formed BGZF chain."""
+    from deepchopper_b200.chop import WRITE_APPEND, WRITE_NO_EOF
+    from deepchopper_b200.encode import FastqIndex
+    rng = np.random.default_rng(10)
+    recs, ix, has, pseqs, ptr, plen, act, n_ad, ad, n_keep, keep = _case(rng, 300)
+    whole = str(tmp_path / "whole.fq.gz")
+    nrec, ntext = write_chopped_fastq(whole, ix, has, ptr, plen, act, n_ad, ad, n_keep, keep, threads=3)
+    parts = str(tmp_path / "parts.fq.gz")
+    open(parts, "wb").close()
+    tot_rec = tot_text = 0
+    cuts = [0, 100, 101, 300]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sub = FastqIndex(ix.buf, *[getattr(ix, f)[a:b] for f in ("name_off", "name_len", "head_len", "seq_off", "seq_len",
+                                                                   "qual_off", "qual_len")])
+        r, t = write_chopped_fastq(parts, sub, has[a:b], ptr[a:b], plen[a:b], act[a:b], n_ad[a:b], ad[a:b], n_keep[a:b],
+                                   keep[a:b], threads=2, flags=WRITE_APPEND | (WRITE_NO_EOF if b < 300 else 0))
+        tot_rec += r
+        tot_text += t
+    assert (tot_rec, tot_text) == (nrec, ntext)
+    raw = open(parts, "rb").read()
+    _check_bgzf(raw)
+    assert gzip.decompress(raw) == gzip.decompress(open(whole, "rb").read())
+
+
+def test_fastq_chunk_reader(tmp_path):
+    """iter_fastq_chunks: pieces of whole records whose concatenation is the file, for plain and gzip input and for a
+    file without trailing newline."""
+    from deepchopper_b200.chop import iter_fastq_chunks
+    rng = np.random.default_rng(0)
+    text = synth.fastq_text(synth.fastq_reads(rng, 500, 20, 400))
+    for name, data, want in (("a.fq", text, text), ("b.fq", text[:-1], text[:-1]), ("c.fq.gz", gzip.compress(text), text)):
+        p = tmp_path / name
+        p.write_bytes(data)
+        for cb in (1000, 7777, 1 << 20):
+            pieces = list(iter_fastq_chunks(str(p), cb))
+            assert b"".join(x.tobytes() for x in pieces) == want
+            assert sum(len(index_fastq(x)) for x in pieces) == 500

@@ -271,3 +271,37 @@ def test_torch_ops_direct():
     lg[:, 1] = torch.from_numpy(lab.astype(np.float32)).to(dev) - 0.5
     out2 = torch.ops.dcb200.smooth_chop(lg, *args[1:], ops.params_list(p))
     assert torch.equal(out2[0], n_ad) and torch.equal(out2[4], act) and torch.equal(out2[1], ad)
+
+
+@pytest.mark.parametrize("ocq", [False, True])
+def test_streaming_chop_equals_whole_file(tmp_path, ocq):
+    """`chop --chunk-mb` (FASTQ streamed in pieces, decisions matched by id, BGZF parts appended) writes the same
+    decompressed bytes and counts as the whole-file driver, for .pt dicts and for compact sidecars; covers a truncated
+    prediction, a read without prediction and a description line."""
+    from deepchopper_b200 import writer
+    from deepchopper_b200.chop import chop_fastq, params_from_cli
+    rng = np.random.default_rng(77)
+    lens = np.concatenate([synth.read_lengths(rng, 200, hi=2500), rng.integers(20, 150, 10)])
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    recs[3] = (recs[3][0] + " some description", recs[3][1], recs[3][2])
+    dicts = _planted_batches(recs, rng)
+    fq_recs = list(recs) + [("nopred", "ACGT" * 50, "I" * 200)]
+    fq_recs[7] = (recs[7][0], recs[7][1] + "ACGTACGT", recs[7][2] + "IIIIIIII")        # prediction shorter than the record
+    fq_path = tmp_path / "reads.fq"
+    fq_path.write_bytes(synth.fastq_text(fq_recs))
+    params = params_from_cli(output_chopped=ocq)
+    pdir, cdir = tmp_path / "predictions", tmp_path / "compact"
+    for i, d in enumerate(dicts):
+        writer.write_batch(str(pdir), 0, i, d)
+        lab = (d["prediction"][..., 1] > d["prediction"][..., 0]).to(torch.uint8)
+        lens_b = (d["target"] != -100).sum(dim=1).numpy()
+        ids = [bytes(d["id"][b, 2:2 + int(d["id"][b, 0])].to(torch.uint8).numpy()).decode("latin1") for b in range(lab.shape[0])]
+        writer.write_batch_compact(str(cdir), 0, i, lab, lens_b, lab.shape[1], ids, d["id"][:, 1].numpy())
+    for name, src in (("pt", pdir), ("compact", cdir)):
+        whole, np1, nr1 = chop_fastq([str(src / "0")], str(fq_path), params, output_prefix=str(tmp_path / f"w_{name}"))
+        part, np2, nr2 = chop_fastq([str(src / "0")], str(fq_path), params, output_prefix=str(tmp_path / f"s_{name}"),
+                                    chunk_bytes=30000, threads=3)
+        assert (np1, nr1) == (np2, nr2)
+        a, b = gzip.open(whole, "rb").read(), gzip.open(part, "rb").read()
+        assert a == b and len(a) > 0
+        assert os.path.basename(part) == f"s_{name}.{np1}pd.{nr1}record.chop.fq.gz"
