@@ -1,4 +1,5 @@
-"""Dump the MLP kernel timeline trace (DCB200_TRACE=1) for one big batch."""
+"""Dump a kernel timeline trace for one big batch: DCB200_TRACE=block|inproj|toeplitz python tools/trace_kernel.py
+(the tracer is compiled in; the env var is read once when the ctx is created)."""
 import ctypes as C
 import os
 import sys
@@ -6,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-os.environ["DCB200_TRACE"] = os.environ.get("DCB200_TRACE", "mlp")
+os.environ["DCB200_TRACE"] = os.environ.get("DCB200_TRACE", "block")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepchopper_b200._native import check, lib  # noqa: E402
 from deepchopper_b200.init_weights import random_state_dict  # noqa: E402
