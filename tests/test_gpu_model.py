@@ -352,3 +352,29 @@ def test_fft_conv_matches_toeplitz_conv(gpu):
         out[kind] = gpu(ids.cuda(), q.cuda()).cpu()
     set_conv(gpu, "auto")
     close("fft vs toeplitz logits", out["fft"], out["toeplitz"], 2e-2, 0.0)
+
+
+def test_conv_kernel_choice_follows_cost_model(gpu):
+    """The product's choice between the two long-convolution kernels (model.cu:use_fft_conv, mirrored by
+    bench.takes_fft for the roofline accounting): Toeplitz below ~6.7 k tokens and while a second FFT block would be
+    mostly empty (8.3 k - 9.9 k), FFT otherwise."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    set_conv(gpu, "auto")
+    ctx = gpu._ctx_now()
+    fft_min = ctx.get_option("fft_min_len")
+    for L in (1024, 6144, 6656, 6784, 8192, 8320, 9856, 9984, 16512):
+        tok = torch.randint(7, 11, (1, L), dtype=torch.uint8, device="cuda")
+        q = torch.rand(1, L, device="cuda")
+        ctx.profile(True)
+        ctx.profile_read(reset=True)
+        gpu.forward_tokens(tok, q, False, True)
+        prof = ctx.profile_read(reset=True)
+        ctx.profile(False)
+        used_fft = "fft_conv" in prof
+        assert used_fft != ("toeplitz_conv" in prof)
+        assert used_fft == bench.takes_fft(L, fft_min), (L, prof.keys())
+    assert not bench.takes_fft(6656, fft_min) and bench.takes_fft(6784, fft_min) and bench.takes_fft(8192, fft_min)
+    assert not bench.takes_fft(8320, fft_min) and bench.takes_fft(9984, fft_min)
