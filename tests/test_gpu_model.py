@@ -378,3 +378,19 @@ def test_conv_kernel_choice_follows_cost_model(gpu):
         assert used_fft == bench.takes_fft(L, fft_min), (L, prof.keys())
     assert not bench.takes_fft(6656, fft_min) and bench.takes_fft(6784, fft_min) and bench.takes_fft(8192, fft_min)
     assert not bench.takes_fft(8320, fft_min) and bench.takes_fft(9984, fft_min)
+
+
+def test_rows_are_independent_bitwise(gpu):
+    """Size-independent property used for the full-size batches that the oracle cannot follow: there is no cross-row
+    operation (no attention mask, every kernel's tiles are row-local), so a row's logits must not depend on which other
+    rows share its batch -- bit for bit, through both long-convolution kernels."""
+    rng = np.random.default_rng(3)
+    for kind, (B, L) in (("toeplitz", (832, 1280)), ("fft", (40, 8192))):
+        set_conv(gpu, kind)
+        ids, q = make_batch(rng, B, L, min_len=L // 2)
+        tok, qd = ids.to(torch.uint8).cuda(), q.cuda()
+        full, lab_full = gpu.forward_tokens(tok, qd, True, True)
+        for lo, hi in ((0, 1), (B // 3, B // 3 + 128), (B - 7, B)):
+            part, lab_part = gpu.forward_tokens(tok[lo:hi].contiguous(), qd[lo:hi].contiguous(), True, True)
+            assert torch.equal(part, full[lo:hi]) and torch.equal(lab_part, lab_full[lo:hi]), (kind, lo, hi)
+    set_conv(gpu, "auto")

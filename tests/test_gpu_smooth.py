@@ -153,3 +153,38 @@ def test_full_size_properties(sm, dcref):
     assert np.array_equal(ad[idx][mm], ref["adapter_iv"][mm])
     mk = np.arange(21)[None, :] < ref["n_keep"][:, None]
     assert np.array_equal(keep[idx][mk], ref["keep_iv"][mk])
+
+
+def test_full_size_properties_chunking_and_order():
+    """Size-independent properties at a size the Python oracle cannot follow (300 k reads, 360 M labels): the result of a
+    read does not depend on how the reads are split over launches nor on their order in the buffer; the C oracle checks
+    a sample bit for bit."""
+    import torch
+    from deepchopper_b200.smooth import smooth_chop_device
+    from oracle import cref
+    rng = np.random.default_rng(123)
+    R = 300_000
+    lens = synth.read_lengths(rng, R)
+    lab, starts, ln = synth.planted_labels_fast(rng, lens)
+    dev = torch.device("cuda", 0)
+    d_lab, d_st, d_ln = torch.from_numpy(lab).to(dev), torch.from_numpy(starts).to(dev), torch.from_numpy(ln).to(dev)
+    whole = [t.cpu().numpy() for t in smooth_chop_device(d_lab, d_st, d_ln)]
+    # (a) ten launches of 30 k reads each == one launch
+    parts = [[t.cpu().numpy() for t in smooth_chop_device(d_lab, d_st[i:i + 30_000].contiguous(), d_ln[i:i + 30_000].contiguous())]
+             for i in range(0, R, 30_000)]
+    for k in range(5):
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k])
+    # (b) reads visited in a random order == the same rows permuted
+    perm = rng.permutation(R)
+    shuffled = [t.cpu().numpy() for t in smooth_chop_device(d_lab, d_st[torch.from_numpy(perm).to(dev)].contiguous(),
+                                                            d_ln[torch.from_numpy(perm).to(dev)].contiguous())]
+    for k in range(5):
+        assert np.array_equal(shuffled[k], whole[k][perm])
+    # (c) a sample against the C oracle
+    idx = np.sort(rng.choice(R, 5000, replace=False))
+    sub_lab = np.concatenate([lab[starts[i]:starts[i] + ln[i]] for i in idx])
+    sub_st = np.concatenate([[0], np.cumsum(ln[idx])[:-1]]).astype(np.int64)
+    chk = cref.load().smooth_chop(sub_lab, sub_st, ln[idx])
+    assert np.array_equal(whole[0][idx], chk["n_adapter"]) and np.array_equal(whole[4][idx], chk["action"])
+    assert np.array_equal(whole[2][idx], chk["n_keep"])
+    assert int(whole[0].sum()) > R // 2       # the planted runs are found
