@@ -192,11 +192,11 @@ __device__ __forceinline__ uint32_t finish_word(const RawWord& r) {
   return r.fast ? (pack16(r.v0) | (pack16(r.v1) << 16)) : r.slow;
 }
 
-__device__ __forceinline__ uint32_t mask_below(int64_t n, int64_t word) {  // bits of word with position < n
-  int64_t lo = word * 32;
-  if (lo + 32 <= n) return 0xffffffffu;
-  if (lo >= n) return 0u;
-  return (1u << (int)(n - lo)) - 1u;
+__device__ __forceinline__ uint32_t mask_below(int n, int word) {  // bits of word with position < n
+  const int d = n - word * 32;  // read positions are 31-bit (lens are int32): no 64-bit arithmetic in the hot loop
+  if (d >= 32) return 0xffffffffu;
+  if (d <= 0) return 0u;
+  return (1u << d) - 1u;
 }
 
 // tie -> keep original; else majority value.  c1 ones among size.
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
   }
   for (int64_t r = warp_global; r < a.R; r += nwarps) {
     const int64_t start = start_n;
-    const int64_t n = n_n;
+    const int n = (int)n_n;
     const RawWord cur = pre;
     start_n = start_nn;
     n_n = n_nn;
@@ -274,23 +274,23 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
         mis = (int)((reinterpret_cast<uintptr_t>(a.labels) + (uintptr_t)start) & 31);
         abase = start - mis;
       }
-      const int64_t NW = n / 32 + 1;  // words 0..n/32 cover positions 0..n (position n closes a trailing run)
-      const int64_t nchunks = (NW + 31) / 32;
+      const int NW = n / 32 + 1;  // words 0..n/32 cover positions 0..n (position n closes a trailing run)
+      const int nchunks = (NW + 31) / 32;
 
       // right-edge window (i + h + 1 > n): [max(0,n-W), n), identical for all such positions; its count of ones is
       // taken from the packed words of the chunk(s) that hold right-edge positions (no extra byte loads)
       const int sizeR = (int)(n < W ? n : W);
       int cR = 0;
-      const int64_t redge = n - h > 0 ? n - h : 0;  // first right-edge position
+      const int redge = n - h > 0 ? n - h : 0;  // first right-edge position
 
       uint32_t A0 = LOGITS ? load_word<LOGITS>(a, abase + 32 * (int64_t)lane, lane <= NW) : finish_word(cur);
       uint32_t prev_word = 0;      // raw word k-1 for lane 0
       uint32_t prev_S_last = 0;    // smoothed bit of position 32k-1 for lane 0
       int open_start = -1;         // most recent run start seen in earlier chunks
 
-      for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t k = 32 * c + lane;
-        uint32_t A1 = load_word<LOGITS>(a, abase + 32 * (k + 32), (k + 32) <= NW);
+      for (int c = 0; c < nchunks; ++c) {
+        const int k = 32 * c + lane;
+        uint32_t A1 = load_word<LOGITS>(a, abase + 32 * (int64_t)(k + 32), (k + 32) <= NW);
         // raw read-relative words
         uint32_t up = __shfl_down_sync(0xffffffffu, A0, 1);
         const uint32_t A1_0 = __shfl_sync(0xffffffffu, A1, 0);
@@ -324,17 +324,17 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
         }
         // right edge: positions >= max(0, n-h) share one window
         if (h > 0 && 1024 * (c + 1) > redge) {  // (warp-uniform) this chunk holds right-edge positions
-          const int64_t lo_pos = n - sizeR;     // window = [lo_pos, n): at most 21 bits, within words 32c-1 .. 32(c+1)
+          const int lo_pos = n - sizeR;         // window = [lo_pos, n): at most 21 bits, within words 32c-1 .. 32(c+1)
           int cnt = __popc(w & ~mask_below(lo_pos, k));
           if (lane == 0 && c > 0) cnt += __popc(wprev & ~mask_below(lo_pos, k - 1));
           if (lane == 31) cnt += __popc(wn0 & ~mask_below(lo_pos, k + 1));
           cR = __reduce_add_sync(0xffffffffu, cnt);
         }
         {
-          const int64_t lo = 32 * k;
+          const int lo = 32 * k;
           if (lo + 32 > redge && h > 0) {
             uint32_t em = mask_below(n, k);
-            if (redge > lo) em &= ~((1u << (int)(redge - lo)) - 1u);
+            if (redge > lo) em &= ~((1u << (redge - lo)) - 1u);
             const int c0 = sizeR - cR;
             const uint32_t val = cR == c0 ? w : (cR > c0 ? 0xffffffffu : 0u);
             S = (S & ~em) | (val & em);
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
         }
         S &= mask_below(n, k);
         if (a.smoothed) {
-          const int64_t lo = 32 * k;
+          const int lo = 32 * k;
           for (int b = 0; b < 32 && lo + b < n; ++b) a.smoothed[start + lo + b] = (int8_t)((S >> b) & 1u);
         }
         if (a.smoothed) {  // majority_voting mode: no interval pass
@@ -352,13 +352,17 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
         if (k == 0) S &= ~1u;  // src/utils.rs:677-684: `start == 0` is the "no open run" sentinel
 
         // ---- runs ------------------------------------------------------------------------------
+        if (!__any_sync(0xffffffffu, S != 0u) && prev_S_last == 0u) {  // nothing starts, nothing ends in this chunk
+          A0 = A1;
+          continue;
+        }
         uint32_t cin = __shfl_up_sync(0xffffffffu, S, 1) >> 31;
         if (lane == 0) cin = prev_S_last;
         prev_S_last = __shfl_sync(0xffffffffu, S, 31) >> 31;
         const uint32_t Sprev = (S << 1) | cin;
         const uint32_t st = S & ~Sprev;
         uint32_t en = ~S & Sprev;
-        const int kbase = (int)(32 * k);
+        const int kbase = 32 * k;
         int scan = st ? kbase + 31 - __clz(st) : -1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
