@@ -302,14 +302,16 @@ def gpu_eager_baseline(sd, seed: int, dev, n_reads: int = 1536):
 
 # ---- our arm -----------------------------------------------------------------------------------------
 
-def takes_fft(L: int, fft_min_len: int) -> bool:
-    """Mirror of model.cu:use_fft_conv (which long-convolution kernel a batch of padded length L takes)."""
-    if L < fft_min_len or L > 32768:
+def takes_fft(L: int, fft_min_len: int, rows: int = 128) -> bool:
+    """Mirror of model.cu:use_fft_conv (which long-convolution kernel a batch of `rows` rows of padded length L takes)."""
+    if L > 32768:
         return False
     if fft_min_len != 6144:
-        return True
+        return L >= fft_min_len
     nb = (L + 8191) // 8192
-    return nb * 8192.0 * (1.57, 1.76, 1.95, 2.06)[nb - 1] / L < 0.29e-3 * L
+    rem = rows % 128
+    tiles = rows // 128 + (1.0 if rem > 64 else (0.5 if rem > 0 else 0.0))
+    return rows * nb * 8192.0 * (1.57, 1.76, 1.95, 2.06)[nb - 1] < tiles * 128.0 * 0.29e-3 * L * L
 
 
 def conv_work(batches, fft_min_len):
@@ -319,7 +321,7 @@ def conv_work(batches, fft_min_len):
     w = {"fft_tokens": 0, "toeplitz_tokens": 0, "toeplitz_flops": 0.0, "fft_flops": 0.0}
     for b in batches:
         t = b.rows.size * b.Lrow
-        if takes_fft(b.Lrow, fft_min_len):
+        if takes_fft(b.Lrow, fft_min_len, int(b.rows.size)):
             w["fft_tokens"] += t
             blocks = (b.Lrow + 8191) // 8192
             w["fft_flops"] += b.rows.size * 256 * blocks * 2 * 5.0 * 8192 * 13
@@ -437,6 +439,45 @@ def extra_stress(model, args, dev, peaks):
             "conv_share": sum(kernels[k]["share"] for k in ("fft_conv", "toeplitz_conv") if k in kernels),
             "kernels": {k: {kk: v.get(kk) for kk in ("ms_total", "launches", "share", "bound", "frac", "ns_per_token_layer",
                                                      "fp32_tflops") if v.get(kk) is not None} for k, v in kernels.items()}}
+
+
+def extra_reference_batching(model, args, dev, n_reads: int = 1536):
+    """The product path in the REFERENCE's batching (configs[0] style: FASTQ order, batch 16, left-pad to the batch
+    maximum; only_fq.py:198-202 + tokenizer.py:34-93) on the read set the GPU eager baseline uses: what a user gets from
+    `predict` without --bucket.  Device-resident and through dcb200_predict_batch_host on pinned host buffers."""
+    from deepchopper_b200 import synth
+    from deepchopper_b200.predict import Batch, HostPipeline
+    rng = np.random.default_rng(args.seed)
+    lens = synth.read_lengths(rng, n_reads, hi=8000)
+    batches = []
+    for i in range(0, n_reads, 16):
+        rows = np.arange(i, min(i + 16, n_reads))
+        lpad = int(lens[rows].max()) + 1
+        batches.append(Batch(rows, lpad, (lpad + 127) // 128 * 128))
+    index_of = {id(b): i for i, b in enumerate(batches)}
+    items = make_items(lens, batches, args.seed + 5, index_of)
+    steps = 3
+    ms, _, launches, pipe = run_pass(model, items, steps, 1, dev, profile=False)
+    del pipe
+    hp = HostPipeline(model)
+    hp.pack_items(items)
+    hp.run_all()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hp.run_all()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    del hp
+    torch.cuda.empty_cache()
+    bases = int(lens.sum())
+    tokens = int(sum(b.rows.size * b.Lrow for b in batches))
+    return {"workload": f"{n_reads} synthetic reads (the GPU eager baseline's read set), FASTQ order, batch 16, left-pad "
+                        "to the batch maximum: the reference's own batching",
+            "value": bases * steps / (ms / 1e3), "unit": UNIT, "ms_per_batch": ms / steps / len(batches),
+            "batches_per_step": len(batches), "steps": steps, "gpu_launches": int(launches),
+            "padded_tokens_per_sec": tokens * steps / (ms / 1e3), "padding_overhead": tokens / max(1, bases),
+            "e2e": {"value": bases * steps / e2e_s, "unit": UNIT, "api": "dcb200_predict_batch_host, one call per batch"}}
 
 
 def extra_smooth_only(args, dev, peaks):
@@ -652,7 +693,8 @@ def run_ours(args, rank, local, world):
     if world == 1 and not args.no_extras:
         extras = {}
         for name, fn in (("stress", lambda: extra_stress(model, args, dev, peaks)),
-                         ("smooth_only", lambda: extra_smooth_only(args, dev, peaks))):
+                         ("smooth_only", lambda: extra_smooth_only(args, dev, peaks)),
+                         ("reference_batching", lambda: extra_reference_batching(model, args, dev))):
             try:
                 extras[name] = fn()
             except Exception as e:  # noqa: BLE001

@@ -69,8 +69,9 @@ struct DevBuf {
 namespace dcb {
 enum KernelKind { K_ENCODE = 0, K_EMBED, K_INPROJ, K_CONV, K_OUTPROJ, K_FC1, K_FC2, K_HEAD1, K_HEAD2, K_SMOOTH, K_OTHER, K_SCONV, K_TOEP, K_MLP, K_BLOCK, K_NKINDS };
 enum TraceKind { TRACE_NONE = 0, TRACE_INPROJ, TRACE_BLOCK, TRACE_TOEPLITZ };
-// Batches shorter than this never take the blocked FFT long convolution (lconv.cu); above it the measured cost model of
-// model.cu:use_fft_conv decides between it and the tensor-core Toeplitz kernel (toeplitz.cu)
+// The default value of the ctx option "fft_min_len" means "let the measured cost model of model.cu:use_fft_conv pick
+// between the blocked FFT long convolution (lconv.cu) and the tensor-core Toeplitz kernel (toeplitz.cu)"; any other
+// value is a plain threshold on the padded batch length
 constexpr int kDefaultFftMinLen = 6144;
 struct ProfRec {
   int kind;

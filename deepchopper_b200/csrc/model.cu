@@ -393,18 +393,24 @@ static int ensure_lconv(dcb200_ctx* ctx, dcb200_weights* w, int L) {
   return DCB200_OK;
 }
 
-// Which long-convolution kernel a batch of padded length L takes.  Measured on B200 (profiles/r02_summary.md, 128 rows):
-// the Toeplitz kernel costs ~0.29 ns per token and layer per 1024 tokens of L (its MMA work grows with L); the FFT kernel
-// costs a fixed time per 8192-token block -- 1.57 / 1.76 / 1.95 / 2.06 ns per token slot for reads of 1 / 2 / 3 / 4 blocks
-// -- whether the last block is full or not.  So the FFT wins from ~6.7 k tokens up to 8192, loses again while a second
-// block is mostly empty (8.3 k - 9.9 k) and wins everywhere above.  An explicit "fft_min_len" option is a plain threshold.
-static bool use_fft_conv(const dcb200_ctx* ctx, int L) {
-  if (L < ctx->fft_min_len || L > lconv_max_len()) return false;
-  if (ctx->fft_min_len != kDefaultFftMinLen) return true;
+// Which long-convolution kernel a batch of B rows of padded length L takes.  Measured on B200 (profiles/r02_summary.md):
+// the Toeplitz kernel works on M-tiles of 128 batch rows and its MMA work grows with L: a full row tile costs ~0.037 ns
+// per token^2 and layer (0.29 ns per token per 1024 tokens of L).  A row tile with at most 64 real rows (the reference's
+// batch 16 is one such tile) costs half of that, 0.0185 ns per token^2: its MMAs run on TMA zero fill, the board leaves
+// its 1 kW power cap and the tensor pipe runs at full clock.  The FFT kernel works per (row, channel) sequence and costs a
+// fixed time per 8192-token block -- 1.57 / 1.76 / 1.95 / 2.06 ns per token slot for reads of 1 / 2 / 3 / 4 blocks --
+// whether the last block is full or not.  With full row tiles the FFT wins from ~6.7 k tokens up to 8192, loses again
+// while a second block is mostly empty (8.3 k - 9.9 k) and wins everywhere above; with 16 rows it wins from ~3.4 k tokens.
+// An explicit "fft_min_len" option is a plain threshold on L.
+static bool use_fft_conv(const dcb200_ctx* ctx, int B, int L) {
+  if (L > lconv_max_len()) return false;
+  if (ctx->fft_min_len != kDefaultFftMinLen) return L >= ctx->fft_min_len;
   static const double kSlotNs[4] = {1.57, 1.76, 1.95, 2.06};
   const int nb = lconv_blocks_for(L);
-  const double fft_ns = nb * 8192.0 * kSlotNs[nb - 1] / L;
-  const double toeplitz_ns = 0.29e-3 * L;
+  const double fft_ns = (double)B * nb * 8192.0 * kSlotNs[nb - 1];
+  const int rem = B % 128;
+  const double tiles = B / 128 + (rem > 64 ? 1.0 : (rem > 0 ? 0.5 : 0.0));
+  const double toeplitz_ns = tiles * 128.0 * 0.29e-3 * L * L;
   return fft_ns < toeplitz_ns;
 }
 
@@ -423,7 +429,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
   // Long convolution: tensor-core Toeplitz GEMMs (MMA work grows with L) below the measured crossover, the blocked
   // shared-memory FFT (O(L log L), fp32) above it (use_fft_conv).  ctx option "fft_min_len" overrides (the tests run both
   // kernels at the same sizes).
-  const bool fft = use_fft_conv(ctx, L);
+  const bool fft = use_fft_conv(ctx, B, L);
   if (fft) DCB_CHECK(ensure_lconv(ctx, w, L));
   else DCB_CHECK(ensure_toeplitz(ctx, w, L));
   const size_t T = (size_t)B * L;

@@ -92,9 +92,11 @@ int dcb200_ctx_sync(dcb200_ctx* ctx);
 void* dcb200_ctx_stream(dcb200_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t dcb200_ctx_launch_count(dcb200_ctx* ctx);
-/* ctx options.  "fft_min_len": reads (padded batch length) at least this long take the blocked shared-memory FFT
+/* ctx options.  "fft_min_len": batches whose padded length is at least this take the blocked shared-memory FFT
  * long convolution (the reference's fftconv, SURVEY Appendix A / deepchopper/models/llm/hyena.py:34-41), shorter
- * ones the tensor-core Toeplitz kernel; default = the measured crossover.  0 = always FFT, a huge value = never.
+ * ones the tensor-core Toeplitz kernel.  The default value (6144) is special: it selects the measured cost model,
+ * which looks at the batch's rows and length (FFT from ~6.7 k tokens with full 128-row tiles, from ~3.4 k tokens
+ * for a 16-row batch).  0 = always FFT, a huge value = never.
  * dcb200_ctx_get_option returns -1 for an unknown name. */
 int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value);
 int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name);

@@ -357,7 +357,8 @@ def test_fft_conv_matches_toeplitz_conv(gpu):
 def test_conv_kernel_choice_follows_cost_model(gpu):
     """The product's choice between the two long-convolution kernels (model.cu:use_fft_conv, mirrored by
     bench.takes_fft for the roofline accounting): Toeplitz below ~6.7 k tokens and while a second FFT block would be
-    mostly empty (8.3 k - 9.9 k), FFT otherwise."""
+    mostly empty (8.3 k - 9.9 k), FFT otherwise; a batch of few rows (the reference's batch 16) fills an eighth of the
+    Toeplitz kernel's 128-row tile and takes the FFT from ~3.4 k tokens."""
     import os
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -365,9 +366,10 @@ def test_conv_kernel_choice_follows_cost_model(gpu):
     set_conv(gpu, "auto")
     ctx = gpu._ctx_now()
     fft_min = ctx.get_option("fft_min_len")
-    for L in (1024, 6144, 6656, 6784, 8192, 8320, 9856, 9984, 16512):
-        tok = torch.randint(7, 11, (1, L), dtype=torch.uint8, device="cuda")
-        q = torch.rand(1, L, device="cuda")
+    for B, L in ((128, 1024), (128, 6144), (128, 6656), (128, 6784), (128, 8192), (128, 8320), (128, 9856), (128, 9984),
+                 (1, 16512), (16, 3200), (16, 3456), (16, 8320), (64, 6144), (200, 6784), (256, 6784)):
+        tok = torch.randint(7, 11, (B, L), dtype=torch.uint8, device="cuda")
+        q = torch.rand(B, L, device="cuda")
         ctx.profile(True)
         ctx.profile_read(reset=True)
         gpu.forward_tokens(tok, q, False, True)
@@ -375,9 +377,10 @@ def test_conv_kernel_choice_follows_cost_model(gpu):
         ctx.profile(False)
         used_fft = "fft_conv" in prof
         assert used_fft != ("toeplitz_conv" in prof)
-        assert used_fft == bench.takes_fft(L, fft_min), (L, prof.keys())
+        assert used_fft == bench.takes_fft(L, fft_min, B), (B, L, prof.keys())
     assert not bench.takes_fft(6656, fft_min) and bench.takes_fft(6784, fft_min) and bench.takes_fft(8192, fft_min)
     assert not bench.takes_fft(8320, fft_min) and bench.takes_fft(9984, fft_min)
+    assert not bench.takes_fft(3200, fft_min, 16) and bench.takes_fft(3456, fft_min, 16)
 
 
 def test_rows_are_independent_bitwise(gpu):
