@@ -1,5 +1,5 @@
-// Persistent, warp-specialised tcgen05 GEMMs with fused epilogues for the classification head (the Hyena layers'
-// projections live in inproj.cu and block.cu).
+// Persistent, warp-specialised tcgen05 GEMM with a fused epilogue for the second half of the classification head (the
+// Hyena layers' projections live in inproj.cu and block.cu, the head's first Linear in head1.cu).
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a 3/4-stage smem ring
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128/256, K=16) into TMEM
@@ -10,7 +10,6 @@
 //               warp fills the other TMEM accumulator stage
 //
 // Modes (reference ops they replace, SURVEY Appendix A / K3,K6,K7,K8):
-//   HEAD1    r = relu(hf . Wh1^T + b1) + q  -> bf16 [T,1024]        (head.py:94-97)
 //   HEAD2    o = relu(r . Wh2^T + b2 + r) ; logits = o . W3^T + b3 ; label = l1 > l0   (head.py:98-102)
 #include "common.cuh"
 #include "ptx.cuh"
@@ -29,7 +28,6 @@ constexpr int kStageBytes = 32 * kStagePitch;       // per epilogue warp
 constexpr int kVecFloats = 3 * 1024;                // column vectors cached in smem (bias / LN gamma,beta / linear3)
 
 template <int MODE> struct Traits;
-template <> struct Traits<G_HEAD1> { static constexpr int K = 256,  NT = 256, INNER = 4, STAGES = 3; };
 template <> struct Traits<G_HEAD2> { static constexpr int K = 1024, NT = 256, INNER = 4, STAGES = 3; };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -91,9 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   // column vectors -> smem (epilogue warps read them as broadcast / lane-fixed float4)
-  if (MODE == G_HEAD1) {
-    for (int i = threadIdx.x; i < 1024; i += kThreads) vec[i] = p.bias[i];
-  } else if (MODE == G_HEAD2) {
+  if (MODE == G_HEAD2) {
     for (int i = threadIdx.x; i < 1024; i += kThreads) {
       vec[i] = p.bias[i];
       vec[1024 + i] = p.w3[i];
@@ -195,46 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * NT + half * HALF + ((uint32_t)(quad * 32) << 16);
 
-        if (MODE == G_HEAD1) {
-          // ---- bf16 output, element-wise epilogue: 64 columns (128 B of bf16) per staged group -------------
-          const size_t own_row = (size_t)tok0 + quad * 32 + lane;
-          const float rowv = __ldg(p.qual + own_row);  // quality of my token row
-#pragma unroll 1
-          for (int grp = 0; grp < HALF / 64; ++grp) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld32(t_row + grp * 64 + c * 32, v);
-              tmem_ld_wait();
-              const float4* b4 = reinterpret_cast<const float4*>(vec + it * NT + half * HALF + grp * 64 + c * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float y[8];
-                const float4 ba = b4[2 * q], bb = b4[2 * q + 1];
-                const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float x = __uint_as_float(v[q * 8 + j]) + bj[j];
-                  y[j] = fmaxf(x, 0.f) + rowv;
-                }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + c * 64 + q * 16),
-                             "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])),
-                             "r"(pack_bf16(y[6], y[7]))
-                             : "memory");
-              }
-            }
-            __syncwarp();
-            // T-layout coalesced store: 4 rows x 128 B per instruction
-            __nv_bfloat16* dst =
-                p.out_bf16 + ((size_t)tok0 + quad * 32 + trow0) * 1024 + it * NT + half * HALF + grp * 64 + piece * 8;
-            constexpr size_t pitch = 1024;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint4 w = *reinterpret_cast<const uint4*>(stg_t + i * 4 * kStagePitch);
-              *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * pitch) = w;
-            }
-            __syncwarp();
-          }
-        } else {  // G_HEAD2
+        {
           const size_t row_t = (size_t)tok0 + quad * 32 + trow0;
 #pragma unroll 1
           for (int c = 0; c < HALF / 32; ++c) {
@@ -320,7 +277,7 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
   const size_t smem = smem_bytes<MODE>();
   DCB_CHECK(ctx->ensure_smem(reinterpret_cast<const void*>(&gemm_kernel<MODE>), smem));
   int grid = p.num_outer < ctx->sm_count ? p.num_outer : ctx->sm_count;
-  ProfScope prof(ctx, MODE == G_HEAD1 ? K_HEAD1 : K_HEAD2);
+  ProfScope prof(ctx, K_HEAD2);
   gemm_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(a, b, p);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
@@ -328,7 +285,6 @@ template <int MODE> static int launch_mode(dcb200_ctx* ctx, const CUtensorMap& a
 
 int launch_gemm(dcb200_ctx* ctx, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p) {
   switch (mode) {
-    case G_HEAD1: return launch_mode<G_HEAD1>(ctx, a, b, p);
     case G_HEAD2: return launch_mode<G_HEAD2>(ctx, a, b, p);
   }
   set_error("bad gemm mode %d", mode);

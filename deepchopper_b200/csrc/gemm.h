@@ -7,15 +7,13 @@ struct dcb200_ctx;
 
 namespace dcb {
 
-enum GemmMode { G_HEAD1 = 2, G_HEAD2 = 3 };
+enum GemmMode { G_HEAD2 = 3 };
 
 struct GemmParams {
   int T;          // tokens = B * L (multiple of 128)
   int L;          // padded read length (multiple of 128)
   int num_outer;  // T / 128 token tiles
   const float* bias;
-  __nv_bfloat16* out_bf16;  // HEAD1: r [T,1024]
-  const float* qual;        // HEAD1: [T]
   const __nv_bfloat16* r_in;  // HEAD2: r [T,1024]
   const float* w3;          // HEAD2: [2,1024]
   const float* b3;          // HEAD2: [2]

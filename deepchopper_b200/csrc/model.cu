@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "block.h"
 #include "gemm.h"
+#include "head1.h"
 #include "inproj.h"
 #include "lconv.h"
 #include "toeplitz.h"
@@ -45,7 +46,7 @@ struct dcb200_weights {
   dcb::LayerW layer[dcb::kLayers];
   __nv_bfloat16 *wh1 = nullptr, *wh2 = nullptr;
   float *bh1 = nullptr, *bh2 = nullptr, *w3 = nullptr, *b3 = nullptr;
-  CUtensorMap tm_h1, tm_h2;
+  CUtensorMap tm_h1, tm_h2;  // tm_h1: boxes of 128 rows (head1.cu), tm_h2: 256 rows (gemm.cu)
   int toep_cap = 0;           // read length the Toeplitz tables were built for
   float2* lc_tw = nullptr;    // twiddle tables of the blocked FFT convolution
   int lc_nbK = 0;             // block distances the filter spectra cover
@@ -316,7 +317,7 @@ static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd)
   DCB_CHECK(upload_f32(ctx, w, sd, "head.linear2.bias", kInner, &w->bh2));
   DCB_CHECK(upload_f32(ctx, w, sd, "head.linear3.weight", 2 * kInner, &w->w3));
   DCB_CHECK(upload_f32(ctx, w, sd, "head.linear3.bias", 2, &w->b3));
-  DCB_CHECK(make_tmap_2d(&w->tm_h1, w->wh1, kInner, kD, 256));
+  DCB_CHECK(make_tmap_2d(&w->tm_h1, w->wh1, kInner, kD, 128));
   DCB_CHECK(make_tmap_2d(&w->tm_h2, w->wh2, kInner, kInner, 256));
   DCB_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging buffers of the caller may now be released
   return DCB200_OK;
@@ -519,19 +520,23 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     DCB_STAGE_DONE();
     DCB_STAGE_DONE();
   }
+  {
+    Head1Params hp;
+    hp.num_pairs = (int)((T + 255) / 256);
+    hp.T = (int)T;
+    hp.bias = w->bh1;
+    hp.qual = qual;
+    CUtensorMap tm_r_st;
+    DCB_CHECK(make_tmap_2d(&tm_r_st, g, T, kInner, 32));
+    DCB_CHECK(launch_head1(ctx, tm_u, w->tm_h1, tm_r_st, hp));
+  }
+  DCB_STAGE_DONE();
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.T = (int)T;
   p.L = L;
   p.num_outer = (int)(T / 128);
-  p.bias = w->bh1;
-  p.qual = qual;
-  p.out_bf16 = g;
-  DCB_CHECK(launch_gemm(ctx, G_HEAD1, tm_u, w->tm_h1, p));
-  DCB_STAGE_DONE();
   p.bias = w->bh2;
-  p.qual = nullptr;
-  p.out_bf16 = nullptr;
   p.r_in = g;
   p.w3 = w->w3;
   p.b3 = w->b3;
