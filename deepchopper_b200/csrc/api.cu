@@ -113,6 +113,11 @@ int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value) {
     ctx->fft_min_len = (int)value;
     return DCB200_OK;
   }
+  if (!strcmp(name, "smooth_warp_kernel")) {
+    DCB_ARG(value == 0 || value == 1);
+    ctx->smooth_warp_kernel = (int)value;
+    return DCB200_OK;
+  }
   set_error("unknown ctx option '%s'", name);
   return DCB200_EINVAL;
 }
@@ -120,6 +125,7 @@ int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value) {
 int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name) {
   if (!ctx || !name) return -1;
   if (!strcmp(name, "fft_min_len")) return ctx->fft_min_len;
+  if (!strcmp(name, "smooth_warp_kernel")) return ctx->smooth_warp_kernel;
   return -1;
 }
 

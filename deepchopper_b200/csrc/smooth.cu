@@ -17,16 +17,18 @@
 
 namespace dcb {
 
+// 4 int8 labels -> bits 28..31 (bit 28 + i = labels[i] == 1), exact for any byte values
+__device__ __forceinline__ uint32_t pack4_top(uint32_t x) {
+  const uint32_t t = x ^ 0x01010101u;  // a zero byte <=> label == 1
+  // bit 7 of every zero byte: (t & 0x7f) + 0x7f sets bit 7 unless the low seven bits are zero (no carry leaves a byte),
+  // or-ing t adds the bytes >= 0x80
+  const uint32_t z = ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
+  return z * 0x00204081u;  // bits 7, 15, 23, 31 -> 28, 29, 30, 31 (the other partial products land below bit 24)
+}
 __device__ __forceinline__ uint32_t pack16(const uint4 v) {
   // 16 int8 labels -> 16 bits (bit i = labels[i] == 1)
-  uint32_t r = 0;
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t e = __vcmpeq4(w[i], 0x01010101u) & 0x01010101u;
-    r |= ((e * 0x01020408u) >> 24) << (4 * i);
-  }
-  return r;
+  return (pack4_top(v.x) >> 28) | ((pack4_top(v.y) >> 24) & 0xf0u) | ((pack4_top(v.z) >> 20) & 0xf00u) |
+         ((pack4_top(v.w) >> 16) & 0xf000u);
 }
 
 #define DCB_FA(a, b, c, s, cy)        \
@@ -203,6 +205,60 @@ __device__ __forceinline__ uint32_t mask_below(int n, int word) {  // bits of wo
 __device__ __forceinline__ uint32_t vote(int c1, int size, uint32_t orig) {
   int c0 = size - c1;
   return c1 == c0 ? orig : (c1 > c0 ? 1u : 0u);
+}
+
+// Per-read tail of both kernels (one thread): the approved-interval rule, the kept intervals and the chop decision.
+__device__ __forceinline__ void finish_read(const SmoothArgs& a, int64_t r, int n, bool skip, int total) {
+  const int approved = a.p.approved_interval_number;
+  if (total > approved) total = 0;  // src/smooth/predict.rs:204-206
+  int nk = 0;
+  uint8_t act = DCB200_ACTION_PASSTHROUGH;
+  const bool qual_ok = !a.qual_lens || a.qual_lens[r] == n;  // src/bin/predict.rs:160-164
+  if (!skip && total > 0 && total <= a.p.max_process_intervals && qual_ok) {
+    if (a.p.output_chopped_seqs) {
+      act = DCB200_ACTION_ADAPTERS;
+    } else {
+      // generate_unmaped_intervals, src/output/split.rs:260-292
+      const int mc = a.p.min_read_length_after_chop;
+      int before = 0, cur = 0, first_len = -1;
+      int32_t* keep = a.keep_iv + r * (approved + 1) * 2;
+      const volatile int32_t* ad = a.adapter_iv + r * approved * 2;
+      for (int i = 0; i < total; ++i) {
+        const int s = ad[2 * i], e = ad[2 * i + 1];
+        if (cur < s) {
+          ++before;
+          if (s - cur >= mc) {
+            keep[2 * nk] = cur;
+            keep[2 * nk + 1] = s;
+            if (nk == 0) first_len = s - cur;
+            ++nk;
+          }
+        }
+        cur = e;
+      }
+      if (cur < n - 1) {
+        ++before;
+        if (n - 1 - cur >= mc) {
+          keep[2 * nk] = cur;
+          keep[2 * nk + 1] = n - 1;
+          if (nk == 0) first_len = n - 1 - cur;
+          ++nk;
+        }
+      }
+      const bool terminal = before == 1;  // src/output/split.rs:185-189
+      const int ct = a.p.chop_type;
+      if ((ct == DCB200_CHOP_TERMINAL && !terminal) || (ct == DCB200_CHOP_INTERNAL && terminal) ||
+          (nk > 0 && first_len == n)) {
+        nk = 0;  // rebuilt, uncut record: src/output/split.rs:191-201
+        act = DCB200_ACTION_UNCHOPPED;
+      } else {
+        act = terminal ? DCB200_ACTION_CHOP_T : DCB200_ACTION_CHOP_I;
+      }
+    }
+  }
+  a.n_adapter[r] = skip ? 0 : total;
+  a.n_keep[r] = nk;
+  a.action[r] = act;
 }
 
 template <bool LOGITS, int HFIX>
@@ -409,58 +465,214 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
     if (a.smoothed) continue;
     __syncwarp();
     // ---- per-read decision (lane 0) ------------------------------------------------------------
-    if (lane == 0) {
-      if (total > approved) total = 0;  // src/smooth/predict.rs:204-206
-      int nk = 0;
-      uint8_t act = DCB200_ACTION_PASSTHROUGH;
-      const bool qual_ok = !a.qual_lens || a.qual_lens[r] == n;  // src/bin/predict.rs:160-164
-      if (!skip && total > 0 && total <= a.p.max_process_intervals && qual_ok) {
-        if (a.p.output_chopped_seqs) {
-          act = DCB200_ACTION_ADAPTERS;
-        } else {
-          // generate_unmaped_intervals, src/output/split.rs:260-292
-          const int mc = a.p.min_read_length_after_chop;
-          int before = 0, cur = 0, first_len = -1;
-          int32_t* keep = a.keep_iv + r * (approved + 1) * 2;
-          const volatile int32_t* ad = a.adapter_iv + r * approved * 2;
-          for (int i = 0; i < total; ++i) {
-            const int s = ad[2 * i], e = ad[2 * i + 1];
-            if (cur < s) {
-              ++before;
-              if (s - cur >= mc) {
-                keep[2 * nk] = cur;
-                keep[2 * nk + 1] = s;
-                if (nk == 0) first_len = s - cur;
-                ++nk;
-              }
-            }
-            cur = e;
-          }
-          if (cur < (int)n - 1) {
-            ++before;
-            if ((int)n - 1 - cur >= mc) {
-              keep[2 * nk] = cur;
-              keep[2 * nk + 1] = (int)n - 1;
-              if (nk == 0) first_len = (int)n - 1 - cur;
-              ++nk;
-            }
-          }
-          const bool terminal = before == 1;  // src/output/split.rs:185-189
-          const int ct = a.p.chop_type;
-          if ((ct == DCB200_CHOP_TERMINAL && !terminal) || (ct == DCB200_CHOP_INTERNAL && terminal) ||
-              (nk > 0 && first_len == (int)n)) {
-            nk = 0;  // rebuilt, uncut record: src/output/split.rs:191-201
-            act = DCB200_ACTION_UNCHOPPED;
-          } else {
-            act = terminal ? DCB200_ACTION_CHOP_T : DCB200_ACTION_CHOP_I;
-          }
+    if (lane == 0) finish_read(a, r, n, skip, total);
+    __syncwarp();
+  }
+}
+
+// ---- tile kernel: int8 labels, windows up to 63, no smoothed-label output ------------------------------------------
+// The warp-per-read kernel above spends its second 1024-base step on 6 of 32 lanes for a typical 1.2 kb read (38
+// lane-words) and pays every per-step cost twice.  Here a CTA owns a tile of 64 consecutive reads and its threads own
+// WORDS (32 bases) of the tile, whatever read they belong to:
+//   P1  thread per aligned raw word: two 16-byte loads, bytes -> bits                              -> A[] (shared)
+//   P2  thread per word: funnel shift by the read's misalignment, mask beyond the read             -> Wd[]
+//       (every read gets one extra all-zero word behind it: the "next word" of the read's last word and the
+//        "previous word" of the following read's first one; there is a zero word in front of the first read too)
+//   P3  thread per word: 21-wide (or generic) majority from Wd[k-1], Wd[k], Wd[k+1]                 -> S[] (over A[])
+//   P4  thread per READ: the clipped windows at the read's two edges, then the scalar run scan over its S words,
+//       interval emission in order and the chop decision (the reference's loops, on 32-base words)
+// A tile whose words do not fit the shared arrays is processed in sub-batches of whole reads.
+constexpr int kTileReads = 64;
+constexpr int kTileThreads = 256;
+constexpr int kTileCap = 3072;                 // a sub-batch = the reads whose first slot falls into one window of kTileCap slots
+constexpr int kTileWords = kTileCap + 1032;    // + the rest of one maximal read (32768 bases: 1025 words + separator) + 2 guards
+
+template <int HFIX>
+__global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothArgs a) {
+  __shared__ __align__(16) uint32_t A[kTileWords];  // raw aligned words, later the smoothed words S
+  __shared__ uint32_t Wd[kTileWords];    // read-relative label words (P1 leaves (read in tile << 11) | word index here)
+  __shared__ int64_t r_start[kTileReads];
+  __shared__ int r_n[kTileReads], r_slots[kTileReads], r_pexcl[kTileReads + 1], r_mis[kTileReads];
+  __shared__ int blk_first[(kTileWords + 31) / 32];  // the read that owns the first slot of every block of 32 slots
+  __shared__ int warp_tot[2];
+  const int tid = threadIdx.x;
+  int window = a.p.smooth_window_size;
+  if ((window & 1) == 0) window += 1;  // src/smooth/utils.rs:50-54
+  const int h = HFIX >= 0 ? HFIX : window / 2;
+  const int W = 2 * h + 1;
+  const int approved = a.p.approved_interval_number;
+  const int64_t n_tiles = (a.R + kTileReads - 1) / kTileReads;
+  const uintptr_t lab0 = reinterpret_cast<uintptr_t>(a.labels);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kTileReads;
+    const int nr = (int)min((int64_t)kTileReads, a.R - r0);
+    // ---- read table: slots per read (n / 32 + 1 words + separator; 0 for reads that are not processed) and their
+    //      exclusive prefix over the tile -------------------------------------------------------------------------------
+    int slots = 0, incl = 0;
+    if (tid < kTileReads) {
+      if (tid < nr) {
+        const int n = a.lens[r0 + tid];
+        const int64_t st = a.starts[r0 + tid];
+        r_start[tid] = st;
+        r_n[tid] = n;
+        r_mis[tid] = (int)((lab0 + (uintptr_t)st) & 31);  // label bytes are fetched as 32-byte aligned groups
+        if (n > 0 && n >= a.p.min_read_length) slots = n / 32 + 2;  // (src/bin/predict.rs:146-148: short reads pass through)
+      }
+      incl = slots;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((tid & 31) >= d) incl += t;
+      }
+      if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < kTileReads) {
+      const int pe = incl - slots + (tid >= 32 ? warp_tot[0] : 0);
+      r_slots[tid] = slots;
+      r_pexcl[tid] = pe;
+      if (tid == kTileReads - 1) r_pexcl[kTileReads] = pe + slots;
+    }
+    __syncthreads();
+    const int all_slots = r_pexcl[kTileReads];
+    // ---- sub-batches: the reads whose first slot lies in [w0, w0 + cap); the last of them may reach beyond ----------
+    for (int w0 = 0; w0 < all_slots; w0 += kTileCap) {
+      // first / last member (reads with slots; a slotless read shares its prefix with the read after it and is skipped
+      // by "largest read whose prefix is <= the slot" as long as the search stops at the last member)
+      int first = -1, last = -1;
+      {
+        const bool mine = tid < kTileReads && r_slots[tid] > 0 && r_pexcl[tid] >= w0 && r_pexcl[tid] < w0 + kTileCap;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (tid < kTileReads && (tid & 31) == 0) warp_tot[tid >> 5] = (int)m;
+        __syncthreads();
+        const unsigned mlo = (unsigned)warp_tot[0], mhi = (unsigned)warp_tot[1];
+        if (mlo | mhi) {
+          first = mlo ? __ffs(mlo) - 1 : 31 + __ffs(mhi);
+          last = mhi ? 63 - __clz(mhi) : 31 - __clz(mlo);
         }
       }
-      a.n_adapter[r] = skip ? 0 : total;
-      a.n_keep[r] = nk;
-      a.action[r] = act;
+      if (first < 0) {  // (the previous sub-batch's last read covered this whole window)
+        __syncthreads();
+        continue;
+      }
+      const int base = r_pexcl[first];
+      const int n_slots = r_pexcl[last] + r_slots[last] - base;  // <= cap + 1027
+      // slot i (0-based) lives at index i + 1 of the shared arrays: index 0 is the zero word in front of the first read
+      if (tid >= first && tid <= last && r_slots[tid] > 0) {
+        const int o0 = r_pexcl[tid] - base;
+        for (int b = (o0 + 31) >> 5; 32 * b < o0 + r_slots[tid]; ++b) blk_first[b] = tid;
+      }
+      __syncthreads();
+      // ---- P1: raw aligned words (also for the separator slot: the last word's funnel shift may need it) ----------
+      for (int i = tid; i < n_slots; i += kTileThreads) {
+        int rr = blk_first[i >> 5];  // owner of slot 32 (i / 32); walk to the last read whose prefix is <= i
+        while (rr < last && r_pexcl[rr + 1] - base <= i) ++rr;
+        const int k = i - (r_pexcl[rr] - base);
+        Wd[i + 1] = (uint32_t)((rr << 11) | k);
+        A[i + 1] = load_word<false>(a, r_start[rr] - r_mis[rr] + 32 * (int64_t)k, true);
+      }
+      if (tid == 0) {
+        A[0] = 0u;
+        A[n_slots + 1] = 0u;
+        Wd[0] = 0u;
+        Wd[n_slots + 1] = 0u;
+      }
+      __syncthreads();
+      // ---- P2: read-relative words -------------------------------------------------------------------------------
+      for (int i = tid; i < n_slots; i += kTileThreads) {
+        const uint32_t m = Wd[i + 1];
+        const int rr = (int)(m >> 11), k = (int)(m & 2047u);
+        const int n = r_n[rr];
+        uint32_t w = 0u;
+        if (k <= n / 32) {
+          const int mis = r_mis[rr];
+          const uint32_t a0 = A[i + 1];
+          w = (mis ? shr_in(a0, A[i + 2], mis) : a0) & mask_below(n, k);
+        }
+        Wd[i + 1] = w;
+      }
+      __syncthreads();
+      // ---- P3: majority vote with full windows (a separator's own value is never read) -----------------------------
+      for (int i = tid; i < n_slots; i += kTileThreads) {
+        const uint32_t w = Wd[i + 1], wp = Wd[i], wn = Wd[i + 2];
+        uint32_t S;
+        if (h == 0) S = w;
+        else if (HFIX == 10) S = majority21(wp, w, wn);
+        else S = majority_generic(wp, w, wn, h);
+        A[i + 1] = S;
+      }
+      __syncthreads();
+      // ---- P4: one thread per read: edges, runs, intervals, decision -------------------------------------------------
+      if (tid >= first && tid <= last && r_slots[tid] > 0) {
+        const int64_t r = r0 + tid;
+        const int n = r_n[tid];
+        const int off = r_pexcl[tid] - base + 1;
+        const int NW = n / 32 + 1;
+        uint32_t* S = A + off;
+        const uint32_t* w = Wd + off;
+        if (h > 0) {
+          // left edge: positions i < h with i + h + 1 <= n use the clipped window [0, i + h + 1)
+          const uint64_t X = ((uint64_t)w[1] << 32) | w[0];
+          uint32_t s0 = S[0];
+          for (int b = 0; b < h && b + h + 1 <= n; ++b) {
+            const int size = b + h + 1;
+            const uint32_t bit = vote(__popcll(X & ((1ull << size) - 1ull)), size, (w[0] >> b) & 1u);
+            s0 = (s0 & ~(1u << b)) | (bit << b);
+          }
+          S[0] = s0;
+          // right edge: positions >= max(0, n - h) share the window [max(0, n - W), n)
+          const int sizeR = n < W ? n : W;
+          const int redge = n - h > 0 ? n - h : 0;
+          const int lo_pos = n - sizeR;
+          int cR = 0;
+          for (int kw = lo_pos / 32; kw <= (n - 1) / 32; ++kw) cR += __popc(w[kw] & ~mask_below(lo_pos, kw));
+          const int c0 = sizeR - cR;
+          for (int kr = redge / 32; kr <= (n - 1) / 32; ++kr) {
+            uint32_t em = mask_below(n, kr);
+            if (redge > 32 * kr) em &= ~((1u << (redge - 32 * kr)) - 1u);
+            const uint32_t val = cR == c0 ? w[kr] : (cR > c0 ? 0xffffffffu : 0u);
+            S[kr] = (S[kr] & ~em) | (val & em);
+          }
+        }
+        S[NW - 1] &= mask_below(n, NW - 1);
+        S[0] &= ~1u;  // src/utils.rs:677-684: `start == 0` is the "no open run" sentinel
+        int total = 0, open_start = -1;
+        uint32_t cin = 0u;
+        for (int k = 0; k < NW; ++k) {
+          // four all-zero words with no run open: nothing starts or ends (most of a read)
+          if (cin == 0u && ((off + k) & 3) == 0 && k + 4 <= NW) {
+            const uint4 q = *reinterpret_cast<const uint4*>(S + k);
+            if ((q.x | q.y | q.z | q.w) == 0u) {
+              k += 3;
+              continue;
+            }
+          }
+          const uint32_t Sk = S[k];
+          const uint32_t Sprev = (Sk << 1) | cin;
+          const uint32_t st = Sk & ~Sprev;
+          cin = Sk >> 31;
+          for (uint32_t e = ~Sk & Sprev; e; e &= e - 1) {
+            const int b = __ffs(e) - 1;
+            const uint32_t below = st & ((1u << b) - 1u);
+            const int s = below ? 32 * k + 31 - __clz(below) : open_start;
+            if (32 * k + b - s >= a.p.min_interval_size) {
+              if (total < approved) {
+                a.adapter_iv[(r * approved + total) * 2 + 0] = s;
+                a.adapter_iv[(r * approved + total) * 2 + 1] = 32 * k + b;
+              }
+              ++total;
+            }
+          }
+          if (st) open_start = 32 * k + 31 - __clz(st);
+        }
+        finish_read(a, r, n, false, total);
+      }
+      __syncthreads();
     }
-    __syncwarp();
+    // reads without label words: shorter than min_read_length (src/bin/predict.rs:146-148) or empty
+    if (tid < nr && r_slots[tid] == 0) finish_read(a, r0 + tid, r_n[tid], r_n[tid] < a.p.min_read_length, 0);
+    __syncthreads();
   }
 }
 
@@ -514,6 +726,16 @@ static int launch_smooth(dcb200_ctx* ctx, SmoothArgs a) {
     a.logits = nullptr;
     a.p.smooth_window_size = 1;
     smooth_chop_kernel<false, -1><<<blocks, threads, 0, ctx->stream>>>(a);
+    DCB_LAUNCH_CHECK(ctx);
+    return DCB200_OK;
+  }
+  if (!logits && !a.smoothed && !ctx->smooth_warp_kernel) {
+    // int8 labels -> coordinates: the tile kernel (thread per 32-base word)
+    const int64_t tiles = (a.R + kTileReads - 1) / kTileReads;
+    const int64_t tcap = (int64_t)ctx->sm_count * 6 * 4;  // 6 resident CTAs per SM (34 KB of shared memory each), a few waves
+    const int tblocks = (int)(tiles < tcap ? tiles : tcap);
+    if (window == 21) smooth_tile_kernel<10><<<tblocks, kTileThreads, 0, ctx->stream>>>(a);
+    else smooth_tile_kernel<-1><<<tblocks, kTileThreads, 0, ctx->stream>>>(a);
     DCB_LAUNCH_CHECK(ctx);
     return DCB200_OK;
   }

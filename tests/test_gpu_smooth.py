@@ -110,6 +110,49 @@ def test_random_ragged_reads_bit_exact(sm, dcref, ps):
         assert np.array_equal(sm_gpu[s:s + l.size], dcref.majority_voting(l, ps["window"]))
 
 
+def test_tile_kernel_sub_batches_and_warp_kernel(sm, dcref):
+    """The int8 path is the tile kernel (thread per 32-base word, 64 reads per CTA): tiles of long reads are split into
+    sub-batches of whole reads, slotless reads (empty / below min_read_length) sit between members, and the last read of
+    a sub-batch may reach beyond its window.  Bit-exact against the C oracle and against the warp-per-read kernel
+    (ctx option smooth_warp_kernel)."""
+    from deepchopper_b200 import ChopParams
+    from deepchopper_b200._native import default_context
+    rng = np.random.default_rng(77)
+    lens = np.concatenate([rng.integers(20000, 32769, 70), rng.integers(0, 200, 40), rng.integers(3000, 9000, 150),
+                           [32768, 0, 32768, 149, 32767, 150, 32736, 1, 32737]])
+    rng.shuffle(lens)
+    lab, starts, ln = synth.planted_labels_fast(rng, lens)
+    lab = lab.copy()
+    lab[rng.random(lab.size) < 0.3] ^= 1          # many short runs as well: every word has starts and ends
+    big = rng.integers(0, lens.size, 12)
+    for r in big:                                  # and some reads that are one long run (the backward search for a start)
+        lab[starts[r]:starts[r] + ln[r]] = 1
+    for ps in (dict(), dict(smooth_window_size=1, min_interval_size=1, approved_interval_number=64, max_process_intervals=64,
+                            min_read_length=0), dict(smooth_window_size=41, min_read_length=0)):
+        p = ChopParams.default(**ps)
+        ctx = default_context()
+        res = sm.smooth_chop_host(lab, starts, ln, p)
+        kw = dict(window=p.smooth_window_size, min_interval=p.min_interval_size, approved=p.approved_interval_number,
+                  max_process=p.max_process_intervals, min_after_chop=p.min_read_length_after_chop,
+                  min_read_len=p.min_read_length, chop_type=p.chop_type, ocq=p.output_chopped_seqs)
+        _compare(res, dcref.smooth_chop(lab, starts, ln, None, **kw))
+        ctx.set_option("smooth_warp_kernel", 1)
+        try:
+            res2 = sm.smooth_chop_host(lab, starts, ln, p)
+        finally:
+            ctx.set_option("smooth_warp_kernel", 0)
+        for k in ("n_adapter", "adapter_iv", "n_keep", "keep_iv", "action"):
+            a, b = getattr(res, k), getattr(res2, k)
+            if k == "adapter_iv":
+                m = np.arange(a.shape[1])[None, :] < res.n_adapter[:, None]
+                assert np.array_equal(a[m], b[m])
+            elif k == "keep_iv":
+                m = np.arange(a.shape[1])[None, :] < res.n_keep[:, None]
+                assert np.array_equal(a[m], b[m])
+            else:
+                assert np.array_equal(a, b), k
+
+
 def test_logits_variant_matches_label_variant(sm):
     import torch
     from deepchopper_b200 import ChopParams
