@@ -208,7 +208,9 @@ __device__ __forceinline__ uint32_t vote(int c1, int size, uint32_t orig) {
 }
 
 // Per-read tail of both kernels (one thread): the approved-interval rule, the kept intervals and the chop decision.
-__device__ __forceinline__ void finish_read(const SmoothArgs& a, int64_t r, int n, bool skip, int total) {
+// `ad`: the read's first `total` adapter intervals (the global table, or a shared-memory copy of its head).
+__device__ __forceinline__ void finish_read(const SmoothArgs& a, int64_t r, int n, bool skip, int total,
+                                            const volatile int32_t* ad) {
   const int approved = a.p.approved_interval_number;
   if (total > approved) total = 0;  // src/smooth/predict.rs:204-206
   int nk = 0;
@@ -222,7 +224,6 @@ __device__ __forceinline__ void finish_read(const SmoothArgs& a, int64_t r, int 
       const int mc = a.p.min_read_length_after_chop;
       int before = 0, cur = 0, first_len = -1;
       int32_t* keep = a.keep_iv + r * (approved + 1) * 2;
-      const volatile int32_t* ad = a.adapter_iv + r * approved * 2;
       for (int i = 0; i < total; ++i) {
         const int s = ad[2 * i], e = ad[2 * i + 1];
         if (cur < s) {
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
     if (a.smoothed) continue;
     __syncwarp();
     // ---- per-read decision (lane 0) ------------------------------------------------------------
-    if (lane == 0) finish_read(a, r, n, skip, total);
+    if (lane == 0) finish_read(a, r, n, skip, total, a.adapter_iv + r * approved * 2);
     __syncwarp();
   }
 }
@@ -482,10 +483,14 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
 //   P4  thread per READ: the clipped windows at the read's two edges, then the scalar run scan over its S words,
 //       interval emission in order and the chop decision (the reference's loops, on 32-base words)
 // A tile whose words do not fit the shared arrays is processed in sub-batches of whole reads.
-constexpr int kTileReads = 64;
-constexpr int kTileThreads = 256;
+// (measured at 2 M reads: 32 reads / 128 threads 1.59 ms, 64 / 128 1.62, 64 / 512 1.76, 128 / 256 1.48, cap 2048 1.63;
+//  64 reads, 256 threads, cap 3072: 1.36 ms)
+constexpr int kTileReads = 64;      // multiple of 32
+constexpr int kTileThreads = 256;   // >= kTileReads
+constexpr int kTileRW = kTileReads / 32;
 constexpr int kTileCap = 3072;                 // a sub-batch = the reads whose first slot falls into one window of kTileCap slots
 constexpr int kTileWords = kTileCap + 1032;    // + the rest of one maximal read (32768 bases: 1025 words + separator) + 2 guards
+constexpr int kIvHead = 4;                     // (the default max_process_intervals: more intervals than that pass the read through)
 
 template <int HFIX>
 __global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothArgs a) {
@@ -493,8 +498,9 @@ __global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothA
   __shared__ uint32_t Wd[kTileWords];    // read-relative label words (P1 leaves (read in tile << 11) | word index here)
   __shared__ int64_t r_start[kTileReads];
   __shared__ int r_n[kTileReads], r_slots[kTileReads], r_pexcl[kTileReads + 1], r_mis[kTileReads];
+  __shared__ int iv_head[kTileReads][2 * kIvHead];  // the first intervals of every read: the decision reads them back
   __shared__ int blk_first[(kTileWords + 31) / 32];  // the read that owns the first slot of every block of 32 slots
-  __shared__ int warp_tot[2];
+  __shared__ int warp_tot[kTileRW];
   const int tid = threadIdx.x;
   int window = a.p.smooth_window_size;
   if ((window & 1) == 0) window += 1;  // src/smooth/utils.rs:50-54
@@ -529,7 +535,8 @@ __global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothA
     }
     __syncthreads();
     if (tid < kTileReads) {
-      const int pe = incl - slots + (tid >= 32 ? warp_tot[0] : 0);
+      int pe = incl - slots;
+      for (int wq = 0; wq < (tid >> 5); ++wq) pe += warp_tot[wq];
       r_slots[tid] = slots;
       r_pexcl[tid] = pe;
       if (tid == kTileReads - 1) r_pexcl[kTileReads] = pe + slots;
@@ -546,10 +553,13 @@ __global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothA
         const unsigned m = __ballot_sync(0xffffffffu, mine);
         if (tid < kTileReads && (tid & 31) == 0) warp_tot[tid >> 5] = (int)m;
         __syncthreads();
-        const unsigned mlo = (unsigned)warp_tot[0], mhi = (unsigned)warp_tot[1];
-        if (mlo | mhi) {
-          first = mlo ? __ffs(mlo) - 1 : 31 + __ffs(mhi);
-          last = mhi ? 63 - __clz(mhi) : 31 - __clz(mlo);
+#pragma unroll
+        for (int wq = 0; wq < kTileRW; ++wq) {
+          const unsigned mw = (unsigned)warp_tot[wq];
+          if (mw) {
+            if (first < 0) first = 32 * wq + __ffs(mw) - 1;
+            last = 32 * wq + 31 - __clz(mw);
+          }
         }
       }
       if (first < 0) {  // (the previous sub-batch's last read covered this whole window)
@@ -661,17 +671,21 @@ __global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothA
                 a.adapter_iv[(r * approved + total) * 2 + 0] = s;
                 a.adapter_iv[(r * approved + total) * 2 + 1] = 32 * k + b;
               }
+              if (total < kIvHead) {
+                iv_head[tid][2 * total] = s;
+                iv_head[tid][2 * total + 1] = 32 * k + b;
+              }
               ++total;
             }
           }
           if (st) open_start = 32 * k + 31 - __clz(st);
         }
-        finish_read(a, r, n, false, total);
+        finish_read(a, r, n, false, total, total <= kIvHead ? iv_head[tid] : a.adapter_iv + r * approved * 2);
       }
       __syncthreads();
     }
     // reads without label words: shorter than min_read_length (src/bin/predict.rs:146-148) or empty
-    if (tid < nr && r_slots[tid] == 0) finish_read(a, r0 + tid, r_n[tid], r_n[tid] < a.p.min_read_length, 0);
+    if (tid < nr && r_slots[tid] == 0) finish_read(a, r0 + tid, r_n[tid], r_n[tid] < a.p.min_read_length, 0, nullptr);
     __syncthreads();
   }
 }
@@ -732,7 +746,7 @@ static int launch_smooth(dcb200_ctx* ctx, SmoothArgs a) {
   if (!logits && !a.smoothed && !ctx->smooth_warp_kernel) {
     // int8 labels -> coordinates: the tile kernel (thread per 32-base word)
     const int64_t tiles = (a.R + kTileReads - 1) / kTileReads;
-    const int64_t tcap = (int64_t)ctx->sm_count * 6 * 4;  // 6 resident CTAs per SM (34 KB of shared memory each), a few waves
+    const int64_t tcap = (int64_t)ctx->sm_count * 24;  // ~6 resident CTAs per SM (36 KB of shared memory each), a few waves
     const int tblocks = (int)(tiles < tcap ? tiles : tcap);
     if (window == 21) smooth_tile_kernel<10><<<tblocks, kTileThreads, 0, ctx->stream>>>(a);
     else smooth_tile_kernel<-1><<<tblocks, kTileThreads, 0, ctx->stream>>>(a);
