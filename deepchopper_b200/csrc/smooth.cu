@@ -30,6 +30,19 @@ __device__ __forceinline__ uint32_t pack16(const uint4 v) {
   return (pack4_top(v.x) >> 28) | ((pack4_top(v.y) >> 24) & 0xf0u) | ((pack4_top(v.z) >> 20) & 0xf00u) |
          ((pack4_top(v.w) >> 16) & 0xf000u);
 }
+// 32 int8 labels -> 32 bits.  When every byte is 0 or 1 (what the classifier writes; checked here, not assumed) a byte IS
+// its bit and a dot product with (1, 2, 4, 8 | 16, 32, 64, 128) gathers eight of them: 13 instructions instead of 65.
+__device__ __forceinline__ uint32_t pack32(const uint4 v0, const uint4 v1) {
+  const uint32_t other = ((v0.x | v0.y | v0.z | v0.w) | (v1.x | v1.y | v1.z | v1.w)) & 0xfefefefeu;
+  if (other == 0u) {
+    const uint32_t b0 = __dp4a(v0.y, 0x80402010u, __dp4a(v0.x, 0x08040201u, 0u));
+    const uint32_t b1 = __dp4a(v0.w, 0x80402010u, __dp4a(v0.z, 0x08040201u, 0u));
+    const uint32_t b2 = __dp4a(v1.y, 0x80402010u, __dp4a(v1.x, 0x08040201u, 0u));
+    const uint32_t b3 = __dp4a(v1.w, 0x80402010u, __dp4a(v1.z, 0x08040201u, 0u));
+    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+  }
+  return pack16(v0) | (pack16(v1) << 16);
+}
 
 #define DCB_FA(a, b, c, s, cy)        \
   {                                   \
@@ -159,7 +172,7 @@ __device__ __forceinline__ uint32_t load_word(const SmoothArgs& a, int64_t g0, b
     } else {
       const uint4* q = reinterpret_cast<const uint4*>(a.labels + g0);  // g0 chosen so the address is 32B aligned
       uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
-      return pack16(v0) | (pack16(v1) << 16);
+      return pack32(v0, v1);
     }
   }
   uint32_t r = 0;
@@ -191,7 +204,7 @@ __device__ __forceinline__ RawWord issue_word(const SmoothArgs& a, int64_t g0, b
   return r;
 }
 __device__ __forceinline__ uint32_t finish_word(const RawWord& r) {
-  return r.fast ? (pack16(r.v0) | (pack16(r.v1) << 16)) : r.slow;
+  return r.fast ? pack32(r.v0, r.v1) : r.slow;
 }
 
 __device__ __forceinline__ uint32_t mask_below(int n, int word) {  // bits of word with position < n
@@ -493,7 +506,7 @@ constexpr int kTileWords = kTileCap + 1032;    // + the rest of one maximal read
 constexpr int kIvHead = 4;                     // (the default max_process_intervals: more intervals than that pass the read through)
 
 template <int HFIX>
-__global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothArgs a) {
+__global__ void __launch_bounds__(kTileThreads, 6) smooth_tile_kernel(const SmoothArgs a) {
   __shared__ __align__(16) uint32_t A[kTileWords];  // raw aligned words, later the smoothed words S
   __shared__ uint32_t Wd[kTileWords];    // read-relative label words (P1 leaves (read in tile << 11) | word index here)
   __shared__ int64_t r_start[kTileReads];
@@ -607,7 +620,7 @@ __global__ void __launch_bounds__(kTileThreads) smooth_tile_kernel(const SmoothA
       for (int i = tid; i < n_slots; i += kTileThreads) {
         const uint32_t w = Wd[i + 1], wp = Wd[i], wn = Wd[i + 2];
         uint32_t S;
-        if (h == 0) S = w;
+        if (h == 0 || (w | wp | wn) == 0u) S = w;  // (no ones within reach: what real predictions mostly look like)
         else if (HFIX == 10) S = majority21(wp, w, wn);
         else S = majority_generic(wp, w, wn, h);
         A[i + 1] = S;

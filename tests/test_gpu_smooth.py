@@ -153,6 +153,23 @@ def test_tile_kernel_sub_batches_and_warp_kernel(sm, dcref):
                 assert np.array_equal(a, b), k
 
 
+def test_label_domain_other_values_count_as_zero(sm):
+    """include/dcb200.h: a label is an adapter base iff it equals 1.  Bytes such as -100 (the ignore index), 2, 3, -1 or 127
+    take the exact packing path (the 0/1 fast path is checked per 32 labels, not assumed) and must behave like 0."""
+    rng = np.random.default_rng(9)
+    lens = synth.read_lengths(rng, 400)
+    lab, starts, ln = synth.planted_labels_fast(rng, lens)
+    weird = lab.copy()
+    zero = np.nonzero(lab == 0)[0]
+    pick = rng.choice(zero, zero.size // 3, replace=False)
+    weird[pick] = rng.choice(np.array([-100, 2, 3, -1, 127, -128, 0x11], dtype=np.int8), pick.size)
+    a = sm.smooth_chop_host(lab, starts, ln)
+    b = sm.smooth_chop_host(weird, starts, ln)
+    for k in ("n_adapter", "adapter_iv", "n_keep", "keep_iv", "action"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(sm.majority_voting_host(weird, starts, ln, 21), sm.majority_voting_host(lab, starts, ln, 21))
+
+
 def test_logits_variant_matches_label_variant(sm):
     import torch
     from deepchopper_b200 import ChopParams
