@@ -114,7 +114,7 @@ int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value) {
     return DCB200_OK;
   }
   if (!strcmp(name, "smooth_warp_kernel")) {
-    DCB_ARG(value == 0 || value == 1);
+    DCB_ARG(value >= 0 && value <= 2);
     ctx->smooth_warp_kernel = (int)value;
     return DCB200_OK;
   }

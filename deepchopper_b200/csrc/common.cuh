@@ -87,7 +87,7 @@ struct dcb200_ctx {
   int64_t launches = 0;
   // options (dcb200_ctx_set_option); the trace kind comes from DCB200_TRACE, read once when the ctx is created
   int fft_min_len = dcb::kDefaultFftMinLen;
-  int smooth_warp_kernel = 0;  // option "smooth_warp_kernel": 1 = int8 labels take the warp-per-read kernel too (tests)
+  int smooth_warp_kernel = 0;  // option "smooth_warp_kernel": 0 = by launch size, 1 = always the warp-per-read kernel, 2 = always the tile kernel
   int trace_kind = dcb::TRACE_NONE;
   bool traced_once = false;
   // named workspaces (activations, staging), grow-only

@@ -756,8 +756,12 @@ static int launch_smooth(dcb200_ctx* ctx, SmoothArgs a) {
     DCB_LAUNCH_CHECK(ctx);
     return DCB200_OK;
   }
-  if (!logits && !a.smoothed && !ctx->smooth_warp_kernel) {
-    // int8 labels -> coordinates: the tile kernel (thread per 32-base word)
+  // int8 labels -> coordinates: the tile kernel (thread per 32-base word) once there is at least a tile of 64 reads per SM;
+  // below that (the ~800-read batches inside predict, a batch of 128 long reads) a CTA per 64 reads leaves the machine
+  // empty and the warp-per-read kernel is 3-4 x faster (15 vs 54 us at 800 reads).  Option smooth_warp_kernel: 1 = never
+  // the tile kernel, 2 = always (tests).
+  const bool tile = ctx->smooth_warp_kernel == 2 || (ctx->smooth_warp_kernel == 0 && a.R >= (int64_t)kTileReads * ctx->sm_count);
+  if (!logits && !a.smoothed && tile) {
     const int64_t tiles = (a.R + kTileReads - 1) / kTileReads;
     const int64_t tcap = (int64_t)ctx->sm_count * 24;  // ~6 resident CTAs per SM (36 KB of shared memory each), a few waves
     const int tblocks = (int)(tiles < tcap ? tiles : tcap);

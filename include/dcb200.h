@@ -97,8 +97,9 @@ int64_t dcb200_ctx_launch_count(dcb200_ctx* ctx);
  * ones the tensor-core Toeplitz kernel.  The default value (6144) is special: it selects the measured cost model,
  * which looks at the batch's rows and length (FFT from ~6.7 k tokens with full 128-row tiles, from ~3.4 k tokens
  * for a 16-row batch).  0 = always FFT, a huge value = never.
- * "smooth_warp_kernel": 1 = dcb200_smooth_chop takes the warp-per-read kernel (the one the logits and smoothed-label
- * forms use) instead of the default tile kernel (thread per 32-base word); both are bit-exact, tests compare them.
+ * "smooth_warp_kernel": which kernel dcb200_smooth_chop takes for int8 labels: 0 (default) = the tile kernel (thread per
+ * 32-base word) when the launch holds at least 64 reads per SM, else the warp-per-read kernel (the one the logits and
+ * smoothed-label forms always use); 1 = always warp-per-read; 2 = always tile.  Both are bit-exact, tests compare them.
  * dcb200_ctx_get_option returns -1 for an unknown name. */
 int dcb200_ctx_set_option(dcb200_ctx* ctx, const char* name, int64_t value);
 int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name);

@@ -20,6 +20,20 @@ def sm():
     return smooth
 
 
+@pytest.fixture(params=[1, 2], ids=["warp_kernel", "tile_kernel"], autouse=True)
+def smooth_kernel(request):
+    """Every test of this module runs once per int8-label kernel (ctx option smooth_warp_kernel: 1 = warp per read,
+    2 = tile; the default picks by launch size and would leave the tile kernel out of the small cases)."""
+    import torch
+    from deepchopper_b200 import _native
+    ctxs = [_native.default_context(), _native.torch_context(torch.device("cuda", 0))]
+    for c in ctxs:
+        c.set_option("smooth_warp_kernel", request.param)
+    yield request.param
+    for c in ctxs:
+        c.set_option("smooth_warp_kernel", 0)
+
+
 @pytest.mark.parametrize("labels,window,expected", MV_KATS)
 def test_majority_voting_kats(sm, labels, window, expected):
     assert sm.majority_voting(labels, window) == expected
@@ -131,16 +145,14 @@ def test_tile_kernel_sub_batches_and_warp_kernel(sm, dcref):
                             min_read_length=0), dict(smooth_window_size=41, min_read_length=0)):
         p = ChopParams.default(**ps)
         ctx = default_context()
+        ctx.set_option("smooth_warp_kernel", 2)
         res = sm.smooth_chop_host(lab, starts, ln, p)
         kw = dict(window=p.smooth_window_size, min_interval=p.min_interval_size, approved=p.approved_interval_number,
                   max_process=p.max_process_intervals, min_after_chop=p.min_read_length_after_chop,
                   min_read_len=p.min_read_length, chop_type=p.chop_type, ocq=p.output_chopped_seqs)
         _compare(res, dcref.smooth_chop(lab, starts, ln, None, **kw))
         ctx.set_option("smooth_warp_kernel", 1)
-        try:
-            res2 = sm.smooth_chop_host(lab, starts, ln, p)
-        finally:
-            ctx.set_option("smooth_warp_kernel", 0)
+        res2 = sm.smooth_chop_host(lab, starts, ln, p)
         for k in ("n_adapter", "adapter_iv", "n_keep", "keep_iv", "action"):
             a, b = getattr(res, k), getattr(res2, k)
             if k == "adapter_iv":

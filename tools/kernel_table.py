@@ -27,7 +27,7 @@ for line in src:
             print(f"  extra[{name}] ERROR {ex['error']}")
             continue
         r = ex.get("roofline") or {}
-        print(f"  extra[{name}] {ex['value']:.4g} {ex['unit']}  ms/step {ex['ms_per_step']:.2f}  roofline {r.get('kernel')} "
+        print(f"  extra[{name}] {ex['value']:.4g} {ex['unit']}  ms/step {ex.get('ms_per_step', float('nan')):.2f}  roofline {r.get('kernel')} "
               f"{r.get('bound')} frac {r.get('frac', 0):.3f}" + (f"  conv share {ex['conv_share']:.3f}" if "conv_share" in ex else "")
               + (f"  e2e {ex['e2e']['value']:.4g}" if "e2e" in ex else ""))
         for k, v in (ex.get("kernels") or {}).items():
