@@ -133,6 +133,10 @@ struct SmoothArgs {
   int32_t* keep_iv;
   uint8_t* action;
   int8_t* smoothed;  // optional: majority_voting output, layout of labels
+  // the warp-per-read kernel as the second launch behind the tile kernel: it visits the reads sel[0 .. *sel_count) only
+  // (those the tile kernel listed because they are longer than its shared arrays hold); null = all reads
+  int32_t* sel;
+  int32_t* sel_count;
 };
 
 template <bool LOGITS>
@@ -304,35 +308,38 @@ __global__ void __launch_bounds__(256) smooth_chop_kernel(const SmoothArgs a) {
     }
     return nn > 0 && ((a.smoothed != nullptr) || nn >= a.p.min_read_length);
   };
-  if (warp_global < a.R) {
-    start_n = a.starts[warp_global];
-    n_n = a.lens[warp_global];
+  const int64_t Rn = a.sel ? (int64_t)*a.sel_count : a.R;            // reads this launch visits
+  auto rid = [&](int64_t i) -> int64_t { return a.sel ? (int64_t)a.sel[i] : i; };
+  if (warp_global < Rn) {
+    start_n = a.starts[rid(warp_global)];
+    n_n = a.lens[rid(warp_global)];
     if (!LOGITS) {
       int mis0;
       int64_t ab0;
       const bool live = plan_read(start_n, n_n, mis0, ab0);
       pre = issue_word(a, ab0 + 32 * (int64_t)lane, live && lane <= n_n / 32 + 1);
     }
-    if (warp_global + nwarps < a.R) {
-      start_nn = a.starts[warp_global + nwarps];
-      n_nn = a.lens[warp_global + nwarps];
+    if (warp_global + nwarps < Rn) {
+      start_nn = a.starts[rid(warp_global + nwarps)];
+      n_nn = a.lens[rid(warp_global + nwarps)];
     }
   }
-  for (int64_t r = warp_global; r < a.R; r += nwarps) {
+  for (int64_t ri = warp_global; ri < Rn; ri += nwarps) {
+    const int64_t r = rid(ri);
     const int64_t start = start_n;
     const int n = (int)n_n;
     const RawWord cur = pre;
     start_n = start_nn;
     n_n = n_nn;
-    if (!LOGITS && r + nwarps < a.R) {
+    if (!LOGITS && ri + nwarps < Rn) {
       int mis1;
       int64_t ab1;
       const bool live = plan_read(start_n, n_n, mis1, ab1);
       pre = issue_word(a, ab1 + 32 * (int64_t)lane, live && lane <= n_n / 32 + 1);
     }
-    if (r + 2 * nwarps < a.R) {
-      start_nn = a.starts[r + 2 * nwarps];
-      n_nn = a.lens[r + 2 * nwarps];
+    if (ri + 2 * nwarps < Rn) {
+      start_nn = a.starts[rid(ri + 2 * nwarps)];
+      n_nn = a.lens[rid(ri + 2 * nwarps)];
     }
     int total = 0;
     const bool skip = (!a.smoothed) && (n < a.p.min_read_length);  // src/bin/predict.rs:146-148
@@ -503,6 +510,7 @@ constexpr int kTileThreads = 256;   // >= kTileReads
 constexpr int kTileRW = kTileReads / 32;
 constexpr int kTileCap = 3072;                 // a sub-batch = the reads whose first slot falls into one window of kTileCap slots
 constexpr int kTileWords = kTileCap + 1032;    // + the rest of one maximal read (32768 bases: 1025 words + separator) + 2 guards
+constexpr int kTileMaxLen = 32768;             // longest read the tile kernel takes (1025 words + separator)
 constexpr int kIvHead = 4;                     // (the default max_process_intervals: more intervals than that pass the read through)
 
 template <int HFIX>
@@ -536,7 +544,9 @@ __global__ void __launch_bounds__(kTileThreads, 6) smooth_tile_kernel(const Smoo
         r_start[tid] = st;
         r_n[tid] = n;
         r_mis[tid] = (int)((lab0 + (uintptr_t)st) & 31);  // label bytes are fetched as 32-byte aligned groups
-        if (n > 0 && n >= a.p.min_read_length) slots = n / 32 + 2;  // (src/bin/predict.rs:146-148: short reads pass through)
+        // (src/bin/predict.rs:146-148: short reads pass through; reads beyond the model's window do not fit the shared
+        //  arrays: launch_smooth sends them through the warp-per-read kernel)
+        if (n > 0 && n >= a.p.min_read_length && n <= kTileMaxLen) slots = n / 32 + 2;
       }
       incl = slots;
 #pragma unroll
@@ -698,7 +708,10 @@ __global__ void __launch_bounds__(kTileThreads, 6) smooth_tile_kernel(const Smoo
       __syncthreads();
     }
     // reads without label words: shorter than min_read_length (src/bin/predict.rs:146-148) or empty
-    if (tid < nr && r_slots[tid] == 0) finish_read(a, r0 + tid, r_n[tid], r_n[tid] < a.p.min_read_length, 0, nullptr);
+    if (tid < nr && r_slots[tid] == 0) {
+      if (r_n[tid] <= kTileMaxLen) finish_read(a, r0 + tid, r_n[tid], r_n[tid] < a.p.min_read_length, 0, nullptr);
+      else a.sel[atomicAdd(a.sel_count, 1)] = (int32_t)(r0 + tid);  // left to the warp-per-read kernel (launch_smooth)
+    }
     __syncthreads();
   }
 }
@@ -762,11 +775,22 @@ static int launch_smooth(dcb200_ctx* ctx, SmoothArgs a) {
   // the tile kernel, 2 = always (tests).
   const bool tile = ctx->smooth_warp_kernel == 2 || (ctx->smooth_warp_kernel == 0 && a.R >= (int64_t)kTileReads * ctx->sm_count);
   if (!logits && !a.smoothed && tile) {
+    DCB_ARG(a.R <= INT_MAX);
+    dcb::DevBuf& sel = ctx->buf("smooth_sel");
+    DCB_CHECK(sel.reserve((size_t)(a.R + 1) * 4));
+    a.sel_count = sel.as<int32_t>();
+    a.sel = a.sel_count + 1;
+    DCB_CUDA(cudaMemsetAsync(a.sel_count, 0, 4, ctx->stream));
     const int64_t tiles = (a.R + kTileReads - 1) / kTileReads;
     const int64_t tcap = (int64_t)ctx->sm_count * 24;  // ~6 resident CTAs per SM (36 KB of shared memory each), a few waves
     const int tblocks = (int)(tiles < tcap ? tiles : tcap);
     if (window == 21) smooth_tile_kernel<10><<<tblocks, kTileThreads, 0, ctx->stream>>>(a);
     else smooth_tile_kernel<-1><<<tblocks, kTileThreads, 0, ctx->stream>>>(a);
+    DCB_LAUNCH_CHECK(ctx);
+    // reads longer than the model's window (possible through the smoothing-only entry points) were listed, not processed:
+    // the warp-per-read kernel, which takes any length, visits exactly those (normally none: it reads the count and exits)
+    if (window == 21) smooth_chop_kernel<false, 10><<<ctx->sm_count, threads, 0, ctx->stream>>>(a);
+    else smooth_chop_kernel<false, -1><<<ctx->sm_count, threads, 0, ctx->stream>>>(a);
     DCB_LAUNCH_CHECK(ctx);
     return DCB200_OK;
   }
@@ -800,6 +824,8 @@ int smooth_chop_device(dcb200_ctx* ctx, const int8_t* labels, const float* logit
   a.keep_iv = keep_iv;
   a.action = action;
   a.smoothed = smoothed;
+  a.sel = nullptr;
+  a.sel_count = nullptr;
   return launch_smooth(ctx, a);
 }
 

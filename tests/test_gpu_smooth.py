@@ -165,6 +165,20 @@ def test_tile_kernel_sub_batches_and_warp_kernel(sm, dcref):
                 assert np.array_equal(a, b), k
 
 
+def test_reads_longer_than_the_model_window(sm, dcref):
+    """The smoothing-only entry points take reads of any length (the tile kernel's shared arrays hold up to 32768 bases per
+    read: longer ones go through the warp-per-read kernel in a second launch behind it)."""
+    from deepchopper_b200._native import default_context
+    rng = np.random.default_rng(31)
+    lens = np.concatenate([rng.integers(200, 3000, 300), [32768, 32769, 40000, 100001, 65536], rng.integers(200, 3000, 100)])
+    lab, starts, ln = synth.planted_labels_fast(rng, lens)
+    ctx = default_context()
+    ctx.set_option("smooth_warp_kernel", 2)
+    res = sm.smooth_chop_host(lab, starts, ln)
+    _compare(res, dcref.smooth_chop(lab, starts, ln))
+    assert res.n_adapter[300:305].sum() > 0
+
+
 def test_label_domain_other_values_count_as_zero(sm):
     """include/dcb200.h: a label is an adapter base iff it equals 1.  Bytes such as -100 (the ignore index), 2, 3, -1 or 127
     take the exact packing path (the 0/1 fast path is checked per 32 labels, not assumed) and must behave like 0."""
