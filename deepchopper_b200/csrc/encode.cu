@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t* __re
   __shared__ float nrm_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int r = blockIdx.x; r < R; r += gridDim.x) {
-    const int n = len[r];
+    // (contract: 0 <= len[r] <= Lpad - 1, include/dcb200.h; the table lives in device memory, so it is clamped here rather
+    //  than trusted: the staging buffers are sized for Lpad - 1 bytes)
+    const int n = max(0, min(len[r], Lpad - 1));
     const uintptr_t sa = reinterpret_cast<uintptr_t>(bytes + seq_off[r]);
     const uintptr_t qa = reinterpret_cast<uintptr_t>(bytes + qual_off[r]);
     const int smis = (int)(sa & 15), qmis = (int)(qa & 15);
