@@ -637,6 +637,17 @@ __global__ void __launch_bounds__(kTileThreads, 6) smooth_tile_kernel(const Smoo
       }
       __syncthreads();
       // ---- P4: one thread per read: edges, runs, intervals, decision -------------------------------------------------
+      // (meanwhile two of the six idle warps pull the label bytes of this CTA's next tile into L2, one request per line)
+      if (w0 == 0 && tid >= kTileThreads - kTileReads && tile + gridDim.x < n_tiles) {
+        const int64_t rn = (tile + gridDim.x) * kTileReads + (tid - (kTileThreads - kTileReads));
+        if (rn < a.R) {
+          const int n = a.lens[rn];
+          if (n >= a.p.min_read_length && n <= kTileMaxLen) {
+            const int8_t* q = a.labels + a.starts[rn];
+            for (int o = 0; o < n; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+          }
+        }
+      }
       if (tid >= first && tid <= last && r_slots[tid] > 0) {
         const int64_t r = r0 + tid;
         const int n = r_n[tid];
