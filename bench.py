@@ -13,7 +13,8 @@ over this rank's part of ONE global synthetic read set:
 `value` is measured with the inputs resident in HBM; `e2e` goes through the C-ABI call on pinned HOST buffers
 (dcb200_predict_batch_host: H2D + compute + D2H inside the timed region; FASTQ parsing / indexing and result files are
 outside it -- tools/bench_cli.py times the file-to-file path).  At N = 1 the line also carries `extra_configs`
-(configs[3] long-read stress sample, configs[4] smooth-only over 10M reads), `gpu_eager_baseline` (the fp32/TF32
+(configs[3] long-read stress sample, configs[4] smooth-only over 10M reads, the product in the reference's own batching:
+FASTQ order, batch 16), `gpu_eager_baseline` (the fp32/TF32
 PyTorch restatement of the reference on the same GPU) and `cpu_baseline`.
 """
 from __future__ import annotations
