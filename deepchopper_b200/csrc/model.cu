@@ -43,6 +43,7 @@ struct dcb200_weights {
   int device = 0;
   int Lmax = 0;
   float* emb = nullptr;  // [16][256]
+  __nv_bfloat16* emb_u = nullptr;  // [16][256]: LayerNorm (norm1 of layer 0, affine folded away) of every embedding row
   dcb::LayerW layer[dcb::kLayers];
   __nv_bfloat16 *wh1 = nullptr, *wh2 = nullptr;
   float *bh1 = nullptr, *bh2 = nullptr, *w3 = nullptr, *b3 = nullptr;
@@ -103,8 +104,42 @@ __global__ void __launch_bounds__(128) implicit_filter_kernel(FilterW w, int Lma
   }
 }
 
-// Embedding gather + LayerNorm1 of layer 0: one warp per token (8 features per lane).
-__global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict__ tok, const float* __restrict__ emb, int T,
+// Embedding + LayerNorm1 of layer 0.  There are 16 token ids, so LayerNorm(embedding row) has 16 possible values: they are
+// computed once per weight set (one warp per id, 8 features per lane) ...
+__global__ void __launch_bounds__(32) embed_table_kernel(const float* __restrict__ emb, __nv_bfloat16* __restrict__ emb_u) {
+  const int lane = threadIdx.x & 31;
+  const int id = blockIdx.x;
+  const float4* e4 = reinterpret_cast<const float4*>(emb + id * kD + lane * 8);
+  const float4 a = __ldg(e4), c = __ldg(e4 + 1);
+  float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s * (1.0f / kD);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v = fmaf(x[i] - mean, x[i] - mean, v);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const float rstd = rsqrtf(v * (1.0f / kD) + 1e-5f);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float y0 = (x[2 * i] - mean) * rstd, y1 = (x[2 * i + 1] - mean) * rstd;  // affine part folded into in_linear
+    __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
+    o[i] = *reinterpret_cast<uint32_t*>(&r);
+  }
+  *reinterpret_cast<uint4*>(emb_u + id * kD + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ... and the per-batch kernel is a gather-copy: one warp per token writes the fp32 residual row (1 KB: two 16-byte
+// stores per lane, each instruction one contiguous 512-byte run) and the bf16 LayerNorm row (512 B: one store per lane)
+// from the two tables (24 KB, L1-resident).  (Writing 32 contiguous bytes per lane as two 16-byte stores made every store
+// instruction cover half of each 32-byte sector: 0.69 of the HBM roofline.)
+__global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict__ tok, const float* __restrict__ emb,
+                                                       const __nv_bfloat16* __restrict__ emb_u, int T,
                                                        float* __restrict__ h, __nv_bfloat16* __restrict__ u) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -112,32 +147,13 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const uint8_t* __restrict
   for (int t = warp; t < T; t += nwarps) {
     int id = tok[t];
     id = id < kVocab ? id : kVocab - 1;
-    const float4* e4 = reinterpret_cast<const float4*>(emb + id * kD + lane * 8);
-    const float4 a = __ldg(e4), c = __ldg(e4 + 1);
-    float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += x[i];
-#pragma unroll
-    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    const float mean = s * (1.0f / kD);
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v = fmaf(x[i] - mean, x[i] - mean, v);
-#pragma unroll
-    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    const float rstd = rsqrtf(v * (1.0f / kD) + 1e-5f);
-    float4* h4 = reinterpret_cast<float4*>(h + (size_t)t * kD + lane * 8);
-    h4[0] = a;
-    h4[1] = c;
-    uint32_t o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float y0 = (x[2 * i] - mean) * rstd, y1 = (x[2 * i + 1] - mean) * rstd;  // affine part folded into in_linear
-      __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
-      o[i] = *reinterpret_cast<uint32_t*>(&r);
-    }
-    *reinterpret_cast<uint4*>(u + (size_t)t * kD + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    const float4* e4 = reinterpret_cast<const float4*>(emb + id * kD);
+    const float4 a = __ldg(e4 + lane), c = __ldg(e4 + 32 + lane);
+    const uint4 y = __ldg(reinterpret_cast<const uint4*>(emb_u + id * kD) + lane);
+    float4* h4 = reinterpret_cast<float4*>(h + (size_t)t * kD);
+    h4[lane] = a;
+    h4[32 + lane] = c;
+    reinterpret_cast<uint4*>(u + (size_t)t * kD)[lane] = y;
   }
 }
 
@@ -257,6 +273,14 @@ int weights_destroy(dcb200_weights* w) {
 
 static int weights_fill(dcb200_ctx* ctx, dcb200_weights* w, const StateDict& sd) {
   DCB_CHECK(upload_f32(ctx, w, sd, "embeddings.word_embeddings.weight", kVocab * kD, &w->emb));
+  {
+    void* eu = nullptr;
+    DCB_CUDA(cudaMalloc(&eu, (size_t)kVocab * kD * sizeof(__nv_bfloat16)));
+    w->allocs.push_back(eu);
+    w->emb_u = static_cast<__nv_bfloat16*>(eu);
+    embed_table_kernel<<<kVocab, 32, 0, ctx->stream>>>(w->emb, w->emb_u);
+    DCB_LAUNCH_CHECK(ctx);
+  }
   // positional table length (= max_seq_len of the checkpoint)
   const int iz = sd.find("layers.0.mixer.filter_fn.pos_emb.z");
   if (iz < 0 || sd.numel[iz] % kEmbDim != 0) {
@@ -482,7 +506,7 @@ int forward_device(dcb200_ctx* ctx, const dcb200_weights* wc, const uint8_t* tok
     const int cap = ctx->sm_count * 8 * 4;
     if (blocks > cap) blocks = cap;
     ProfScope prof(ctx, K_EMBED);
-    embed_ln_kernel<<<blocks, 256, 0, ctx->stream>>>(tok, w->emb, (int)T, hA, u);
+    embed_ln_kernel<<<blocks, 256, 0, ctx->stream>>>(tok, w->emb, w->emb_u, (int)T, hA, u);
     DCB_LAUNCH_CHECK(ctx);
   }
   DCB_STAGE_DONE();
