@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("DCB200_LIB") or os.path.join(_HERE, "lib", "libdcb200
 
 EXPORTS = [
     "dcb200_last_error", "dcb200_version", "dcb200_chop_params_default", "dcb200_ctx_create", "dcb200_ctx_destroy",
-    "dcb200_ctx_sync", "dcb200_ctx_stream", "dcb200_ctx_launch_count", "dcb200_encode_batch", "dcb200_weights_create",
+    "dcb200_ctx_sync", "dcb200_ctx_stream", "dcb200_ctx_launch_count", "dcb200_encode_batch", "dcb200_encode_batch_rows", "dcb200_weights_create",
     "dcb200_weights_destroy", "dcb200_forward", "dcb200_smooth_chop", "dcb200_smooth_chop_logits",
     "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
@@ -78,6 +78,7 @@ def lib():
     l.dcb200_ctx_get_option.argtypes = [vp, C.c_char_p]
     l.dcb200_ctx_get_option.restype = i64
     l.dcb200_encode_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    l.dcb200_encode_batch_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     l.dcb200_weights_create.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(vp)]
     l.dcb200_weights_destroy.argtypes = [vp]
     l.dcb200_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]

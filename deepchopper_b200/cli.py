@@ -105,7 +105,6 @@ class BatchWriter:
 def _predict_worker(rank: int, world: int, args, shared):
     import torch
     from . import encode, writer
-    from .encode import encode_batch_device
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
     model = _load_model(args, dev)
@@ -119,30 +118,45 @@ def _predict_worker(rank: int, world: int, args, shared):
     mine = plan_rank_batches(lens, args, rank, world)
     t0 = time.time()
     bw = BatchWriter(dev)
-    for idx, b in mine:
-        ln = lens[b.rows]
+    from . import ops  # noqa: F401  (registers torch.ops.dcb200.*)
+    from .predict import Launch, group_batches
+    if args.bucket:
+        launches = [Launch(b.rows, np.full(b.rows.size, b.Lpad, np.int32), b.Lpad, b.Lrow, [(k, 0, b.rows.size, b)])
+                    for k, (_, b) in enumerate(mine)]
+    else:
+        # the reference's FASTQ-order batches of --batch-size reads, many per launch: every row keeps the pad count of
+        # its own batch (the pads are semantic), the kernels get full row tiles, and one .pt per reference batch is written
+        launches = group_batches([b for _, b in mine], args.token_budget)
+    for g in launches:
+        ln = lens[g.rows]
         tot = int(ln.sum())
         host = torch.empty(2 * tot, dtype=torch.uint8).pin_memory()
         hb = host.numpy()
-        hb[:tot] = gather_ranges(ix.buf, ix.seq_off[b.rows], ln)
-        hb[tot:] = gather_ranges(ix.buf, ix.qual_off[b.rows], ln)
+        hb[:tot] = gather_ranges(ix.buf, ix.seq_off[g.rows], ln)
+        hb[tot:] = gather_ranges(ix.buf, ix.qual_off[g.rows], ln)
         so = np.cumsum(ln) - ln
         blob = host.to(dev, non_blocking=True)
-        tok, qual = encode_batch_device(blob, torch.from_numpy(so).to(dev), torch.from_numpy(so + tot).to(dev),
-                                        torch.from_numpy(ln.astype(np.int32)).to(dev), b.Lpad, None, b.Lrow)
-        ids = [ix.name(r) for r in b.rows]
+        tok, qual = torch.ops.dcb200.encode_rows(blob, torch.from_numpy(so).to(dev), torch.from_numpy(so + tot).to(dev),
+                                                 torch.from_numpy(ln.astype(np.int32)).to(dev),
+                                                 torch.from_numpy(g.lpad).to(dev), int(g.Lpad), int(g.Lrow))
         if args.compact:   # labels only, bit-packed: read back by this package's `chop`
-            _, labels = model.forward_tokens(tok, qual, False, True)
-            bw.submit(lambda labels=labels, ln=ln, b=b, idx=idx, ids=ids, host=host: writer.write_batch_compact(
-                args.output, rank, idx, labels, ln, b.Lpad, ids, truncated[b.rows]))
-            continue
-        logits, _ = model.forward_tokens(tok, qual, True, False)
-        id_rows = encode.id_rows(ix, b.rows, truncated[b.rows])
-        bw.submit(lambda logits=logits, tok=tok, qual=qual, id_rows=id_rows, ln=ln, b=b, idx=idx, host=host: writer.write_batch(
-            args.output, rank, idx, writer.batch_dict(logits, tok, qual, id_rows, ln, b.Lpad)))
+            logits, labels = None, model.forward_tokens(tok, qual, False, True)[1]
+        else:
+            logits, labels = model.forward_tokens(tok, qual, True, False)[0], None
+        for pos, r0, r1, b in g.members:
+            idx = mine[pos][0]
+            lnb = ln[r0:r1]
+            if args.compact:
+                ids = [ix.name(r) for r in b.rows]
+                bw.submit(lambda labels=labels[r0:r1], lnb=lnb, b=b, idx=idx, ids=ids, host=host: writer.write_batch_compact(
+                    args.output, rank, idx, labels, lnb, b.Lpad, ids, truncated[b.rows]))
+                continue
+            id_rows = encode.id_rows(ix, b.rows, truncated[b.rows])
+            bw.submit(lambda logits=logits[r0:r1], tok=tok[r0:r1], qual=qual[r0:r1], id_rows=id_rows, lnb=lnb, b=b, idx=idx,
+                      host=host: writer.write_batch(args.output, rank, idx, writer.batch_dict(logits, tok, qual, id_rows, lnb, b.Lpad)))
     bw.close()
     if args.verbose:
-        print(f"[rank {rank}] {len(mine)} batches in {time.time() - t0:.2f}s", file=sys.stderr)
+        print(f"[rank {rank}] {len(mine)} batches in {len(launches)} launches, {time.time() - t0:.2f}s", file=sys.stderr)
 
 
 def cmd_predict(args):

@@ -17,7 +17,8 @@ void set_error(const char* fmt, ...) {
 }
 
 int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
-                  const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual);
+                  const int32_t* len, const int32_t* lpad_rows, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok,
+                  float* qual);
 int smooth_chop_device(dcb200_ctx* ctx, const int8_t* labels, const float* logits, int64_t total, const int64_t* starts,
                        const int32_t* lens, const int32_t* qual_lens, int64_t R, const dcb200_chop_params* p,
                        int32_t* n_adapter, int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv, uint8_t* action,
@@ -159,7 +160,17 @@ int dcb200_encode_batch(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* se
   DCB_ARG(R >= 0 && Lpad > 0 && Lrow >= Lpad && Lrow % 4 == 0);
   DCB_ARG((reinterpret_cast<uintptr_t>(tok) & 3) == 0 && (reinterpret_cast<uintptr_t>(qual) & 15) == 0);
   DCB_CUDA(cudaSetDevice(ctx->device));
-  return encode_device(ctx, bytes, seq_off, qual_off, len, R, Lpad, Lrow, tok, qual);
+  return encode_device(ctx, bytes, seq_off, qual_off, len, nullptr, R, Lpad, Lrow, tok, qual);
+}
+
+int dcb200_encode_batch_rows(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
+                             const int32_t* len, const int32_t* lpad_rows, int32_t R, int32_t Lpad, int32_t Lrow,
+                             uint8_t* tok, float* qual) {
+  DCB_ARG(ctx && bytes && seq_off && qual_off && len && lpad_rows && tok && qual);
+  DCB_ARG(R >= 0 && Lpad > 0 && Lrow >= Lpad && Lrow % 4 == 0);
+  DCB_ARG((reinterpret_cast<uintptr_t>(tok) & 3) == 0 && (reinterpret_cast<uintptr_t>(qual) & 15) == 0);
+  DCB_CUDA(cudaSetDevice(ctx->device));
+  return encode_device(ctx, bytes, seq_off, qual_off, len, lpad_rows, R, Lpad, Lrow, tok, qual);
 }
 
 int dcb200_weights_create(dcb200_ctx* ctx, const char* const* names, const float* const* data, const int64_t* numel,
@@ -399,7 +410,7 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   DCB_CHECK(stage_out(ctx, "h_act", (size_t)R, &d_act));
   DCB_CUDA(cudaMemsetAsync(d_ad, 0, (size_t)R * ap * 8, ctx->stream));
   DCB_CUDA(cudaMemsetAsync(d_kp, 0, (size_t)R * (ap + 1) * 8, ctx->stream));
-  DCB_CHECK(encode_device(ctx, (const uint8_t*)d_bytes, (const int64_t*)d_so, (const int64_t*)d_qo, (const int32_t*)d_len, R,
+  DCB_CHECK(encode_device(ctx, (const uint8_t*)d_bytes, (const int64_t*)d_so, (const int64_t*)d_qo, (const int32_t*)d_len, nullptr, R,
                           Lpad, Lrow, (uint8_t*)d_tok, (float*)d_q));
   DCB_CHECK(forward_device(ctx, w, (const uint8_t*)d_tok, (const float*)d_q, R, Lrow, (float*)d_logits, (uint8_t*)d_lab, 1 << 30));
   DCB_CHECK(smooth_chop_device(ctx, (const int8_t*)d_lab, nullptr, (int64_t)T, (const int64_t*)d_st, (const int32_t*)d_len,

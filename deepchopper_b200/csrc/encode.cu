@@ -34,6 +34,7 @@ constexpr int kEncThreads = 256;
 
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ seq_off,
                                                              const int64_t* __restrict__ qual_off, const int32_t* __restrict__ len,
+                                                             const int32_t* __restrict__ lpad_rows,
                                                              int32_t R, int32_t Lpad, int32_t Lrow, int32_t cap16,
                                                              uint8_t* __restrict__ tok, float* __restrict__ qual) {
   extern __shared__ uint4 enc_smem[];   // [2][cap16] 16-byte words: sequence, quality
@@ -43,7 +44,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t* __re
   for (int r = blockIdx.x; r < R; r += gridDim.x) {
     // (contract: 0 <= len[r] <= Lpad - 1, include/dcb200.h; the table lives in device memory, so it is clamped here rather
     //  than trusted: the staging buffers are sized for Lpad - 1 bytes)
-    const int n = max(0, min(len[r], Lpad - 1));
+    // per-row collated length (several of the reference's batches in one launch, dcb200_encode_batch_rows), else the launch's
+    const int lp = lpad_rows ? max(1, min(lpad_rows[r], Lpad)) : Lpad;
+    const int n = max(0, min(len[r], lp - 1));
     const uintptr_t sa = reinterpret_cast<uintptr_t>(bytes + seq_off[r]);
     const uintptr_t qa = reinterpret_cast<uintptr_t>(bytes + qual_off[r]);
     const int smis = (int)(sa & 15), qmis = (int)(qa & 15);
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t* __re
     }
     __syncthreads();
     const float nrm = nrm_s;
-    const int pad = Lpad - (n + 1);
+    const int pad = lp - (n + 1);
     uint32_t* trow = reinterpret_cast<uint32_t*>(tok + (int64_t)r * Lrow);
     float4* qrow = reinterpret_cast<float4*>(qual + (int64_t)r * Lrow);
     for (int c4 = tid; c4 < Lrow / 4; c4 += kEncThreads) {
@@ -117,7 +120,8 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t* __re
 }
 
 int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
-                  const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual) {
+                  const int32_t* len, const int32_t* lpad_rows, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok,
+                  float* qual) {
   if (R == 0) return DCB200_OK;
   // staging: two strings of at most Lpad - 1 bytes, each with up to 15 bytes of alignment slack on either side
   const int cap16 = (Lpad + 15 + 15) / 16 + 1;
@@ -127,7 +131,8 @@ int encode_device(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off,
   const int cap = ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
   ProfScope prof(ctx, K_ENCODE);
-  encode_kernel<<<blocks, kEncThreads, smem, ctx->stream>>>(bytes, seq_off, qual_off, len, R, Lpad, Lrow, cap16, tok, qual);
+  encode_kernel<<<blocks, kEncThreads, smem, ctx->stream>>>(bytes, seq_off, qual_off, len, lpad_rows, R, Lpad, Lrow, cap16, tok,
+                                                            qual);
   DCB_LAUNCH_CHECK(ctx);
   return DCB200_OK;
 }

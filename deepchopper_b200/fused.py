@@ -19,7 +19,7 @@ import torch
 from ._native import ChopParams
 from .chop import write_chopped_fastq
 from .encode import MAX_TOKENS, encode_batch_device, index_fastq, read_fastq_bytes
-from .predict import plan_batches
+from .predict import group_batches, plan_batches
 from .smooth import smooth_chop_device
 
 
@@ -38,7 +38,9 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
                        max_sample: Optional[int] = None, verbose: bool = False, preloaded=None) -> Tuple[str, int, int]:
     """FASTQ -> ``{prefix|stem}.{n_pred}pd.{n_out}record.chop.fq.gz``.  ``batch_size`` = None: length-bucketed batches of
     ~``token_budget`` padded tokens; an integer: the reference's FASTQ-order batches of that many reads (left pads are
-    semantic, so the two give different logits near ties -- like any change of batch size in the reference).
+    semantic, so the two give different logits near ties -- like any change of batch size in the reference).  Those small
+    batches are packed into launches of ~``token_budget`` tokens in which every row keeps the pad count of its own batch
+    (``predict.group_batches``): same inputs per read as the reference's collation, full row tiles for the kernels.
     ``preloaded`` = (bytes, FastqIndex) when the caller already read and indexed the file (the CLI does that on a thread
     while CUDA and the weights come up).  Returns (output path, #predictions, #records written)."""
     t0 = time.time()
@@ -54,10 +56,12 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
     lens = np.minimum(ix.seq_len[:n].astype(np.int64), MAX_TOKENS - 1)       # tokenizer.py:154-163 (truncation)
     if batch_size is None:
         batches = plan_batches(lens, token_budget=token_budget)
+        # largest batch first: the library's grow-only workspaces are sized once (a regrowth frees and reallocates GBs)
+        batches = sorted(batches, key=lambda b: -b.rows.size * b.Lrow)
+        launches = None
     else:
         batches = plan_batches(lens, token_budget=1 << 62, max_rows=int(batch_size), sort=False)
-    # largest batch first: the library's grow-only workspaces are sized once (a regrowth frees and reallocates GBs)
-    batches = sorted(batches, key=lambda b: -b.rows.size * b.Lrow)
+        launches = sorted(group_batches(batches, token_budget), key=lambda g: -g.rows.size * g.Lrow)
     t_index = time.time()
     blob = torch.from_numpy(buf).to(dev)
     torch.cuda.synchronize(dev)
@@ -68,15 +72,22 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
     qlen_dev = torch.from_numpy(np.ascontiguousarray(ix.qual_len[:n].astype(np.int32))).to(dev)
     outs = []
     t_first = None
-    for b in batches:
+    from . import ops  # noqa: F401  (registers torch.ops.dcb200.*)
+    for b in (launches if launches is not None else batches):
         if verbose and len(outs) == 1:
             torch.cuda.synchronize(dev)      # (verbose only) first batch = one-time costs: kernel loading, Toeplitz tables
             t_first = time.time()
         rows = torch.from_numpy(b.rows).to(dev)
         ln = lens_dev[rows]
-        tok, qual = encode_batch_device(blob, seq_off[rows], qual_off[rows], ln, b.Lpad, None, b.Lrow)
+        if launches is None:
+            tok, qual = encode_batch_device(blob, seq_off[rows], qual_off[rows], ln, b.Lpad, None, b.Lrow)
+            lpad64 = b.Lpad
+        else:
+            lpad = torch.from_numpy(b.lpad).to(dev)
+            tok, qual = torch.ops.dcb200.encode_rows(blob, seq_off[rows], qual_off[rows], ln, lpad, int(b.Lpad), int(b.Lrow))
+            lpad64 = lpad.to(torch.int64)
         _, labels = model.forward_tokens(tok, qual, False, True)
-        starts = torch.arange(b.rows.size, dtype=torch.int64, device=dev) * b.Lrow + (b.Lpad - 1) - ln.to(torch.int64)
+        starts = torch.arange(b.rows.size, dtype=torch.int64, device=dev) * b.Lrow + (lpad64 - 1) - ln.to(torch.int64)
         # a read cut to the model's window has qual_len != predicted length -> passthrough (src/bin/predict.rs:160-164)
         outs.append(smooth_chop_device(labels.view(-1), starts, ln, params, qlen_dev[rows]))
     # host work that does not need the GPU's results runs while the batches above are still executing
@@ -92,7 +103,7 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
     ad_all = np.zeros((R, max(1, approved), 2), np.int32)
     keep_all = np.zeros((R, approved + 1, 2), np.int32)
     if batches:
-        order = np.concatenate([b.rows for b in batches])
+        order = np.concatenate([b.rows for b in (launches if launches is not None else batches)])
         n_ad, ad, n_keep, keep, act = (torch.cat([o[i] for o in outs]).cpu().numpy() for i in range(5))
         has_pred[order] = 1
         action[order] = act
@@ -120,7 +131,7 @@ def predict_chop_fastq(fq: str, model, params: Optional[ChopParams] = None, outp
         rss = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
         bases = int(lens.sum())
         t1 = time.time()
-        print(f"predict+chop: {n} reads, {bases} bases, {len(batches)} batches -> {n_out} records ({n_text} text bytes); "
+        print(f"predict+chop: {n} reads, {bases} bases, {len(batches)} batches{"" if launches is None else f" in {len(launches)} launches"} -> {n_out} records ({n_text} text bytes); "
               f"read+index {t_index - t0:.2f} s, upload {t_up - t_index:.2f} s, first batch {(t_first or t_gpu) - t_up:.2f} s, "
               f"other batches + results {t_gpu - (t_first or t_gpu):.2f} s, write {t1 - t_gpu:.2f} s, "
               f"{bases / (t1 - t0) / 1e6:.1f} M bases/s wall, peak RSS {rss:.0f} MB")

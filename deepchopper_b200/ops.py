@@ -53,6 +53,8 @@ def _p(t):
 
 _LIB = torch.library.Library("dcb200", "DEF")
 _LIB.define("encode(Tensor blob, Tensor seq_off, Tensor qual_off, Tensor lens, int Lpad, int Lrow) -> (Tensor, Tensor)")
+_LIB.define("encode_rows(Tensor blob, Tensor seq_off, Tensor qual_off, Tensor lens, Tensor lpad_rows, int Lpad, int Lrow) -> "
+            "(Tensor, Tensor)")
 _LIB.define("forward(Tensor tok, Tensor qual, int weights, bool want_logits, bool want_labels) -> (Tensor, Tensor)")
 _LIB.define("smooth_chop(Tensor labels, Tensor starts, Tensor lens, Tensor qual_lens, int[] params) -> "
             "(Tensor, Tensor, Tensor, Tensor, Tensor)")
@@ -72,6 +74,26 @@ def encode(blob: torch.Tensor, seq_off: torch.Tensor, qual_off: torch.Tensor, le
 
 
 def _encode_meta(blob, seq_off, qual_off, lens, Lpad, Lrow):
+    R = lens.numel()
+    return blob.new_empty((R, Lrow), dtype=torch.uint8), blob.new_empty((R, Lrow), dtype=torch.float32)
+
+
+def encode_rows(blob: torch.Tensor, seq_off: torch.Tensor, qual_off: torch.Tensor, lens: torch.Tensor,
+                lpad_rows: torch.Tensor, Lpad: int, Lrow: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """dcb200_encode_batch_rows: every row left-padded to ITS OWN collated length (several reference batches, one launch)."""
+    assert blob.dtype == torch.uint8 and seq_off.dtype == torch.int64 and qual_off.dtype == torch.int64
+    assert lens.dtype == torch.int32 and lpad_rows.dtype == torch.int32 and lpad_rows.numel() == lens.numel()
+    assert blob.is_contiguous() and seq_off.is_contiguous() and qual_off.is_contiguous() and lpad_rows.is_contiguous()
+    R = int(lens.numel())
+    tok = torch.empty((R, Lrow), dtype=torch.uint8, device=blob.device)
+    qual = torch.empty((R, Lrow), dtype=torch.float32, device=blob.device)
+    ctx = _native.torch_context(blob.device)
+    check(lib().dcb200_encode_batch_rows(ctx.handle, _p(blob), _p(seq_off), _p(qual_off), _p(lens), _p(lpad_rows), R, int(Lpad),
+                                         int(Lrow), _p(tok), _p(qual)))
+    return tok, qual
+
+
+def _encode_rows_meta(blob, seq_off, qual_off, lens, lpad_rows, Lpad, Lrow):
     R = lens.numel()
     return blob.new_empty((R, Lrow), dtype=torch.uint8), blob.new_empty((R, Lrow), dtype=torch.float32)
 
@@ -131,7 +153,8 @@ def _smooth_chop_meta(labels, starts, lens, qual_lens, params):
             lens.new_empty(R, **i32), lens.new_empty((R, ap + 1, 2), **i32), lens.new_empty(R, dtype=torch.uint8))
 
 
-for _name, _cuda, _meta in (("encode", encode, _encode_meta), ("forward", forward, _forward_meta),
+for _name, _cuda, _meta in (("encode", encode, _encode_meta), ("encode_rows", encode_rows, _encode_rows_meta),
+                            ("forward", forward, _forward_meta),
                             ("smooth_chop", smooth_chop, _smooth_chop_meta)):
     _LIB.impl(_name, _cuda, "CUDA")     # CUDA only: a CPU tensor finds no kernel (no fallback)
     _LIB.impl(_name, _meta, "Meta")

@@ -77,6 +77,60 @@ def plan_batches(lens: np.ndarray, token_budget: int = 1024 * 1024, max_rows: in
     return batches
 
 
+@dataclass
+class Launch:
+    """Several of the reference's FASTQ-order batches in one launch (dcb200_encode_batch_rows): every row keeps the pad
+    count of ITS batch -- the pads are semantic -- while the kernels see full 128-row tiles instead of 12-16 rows."""
+    rows: np.ndarray      # read indices, member after member
+    lpad: np.ndarray      # int32 per row: collated length of the row's own batch
+    Lpad: int             # max(lpad)
+    Lrow: int             # row stride, multiple of 128
+    members: list         # [(position of the batch in the input list, first row, one past the last row, Batch)]
+
+
+def group_batches(batches: Sequence[Batch], token_budget: int = 1024 * 1024) -> List[Launch]:
+    """Pack FASTQ-order batches into launches of about ``token_budget`` padded tokens, batches of similar padded length
+    together (a row is right-filled to the longest member's stride).  Results per read are those of the reference's own
+    batching: the model is causal and rows are independent, so what a row sees in its first ``lpad`` columns does not
+    depend on its neighbours in the launch."""
+    order = sorted(range(len(batches)), key=lambda i: (batches[i].Lrow, i))
+    out: List[Launch] = []
+    cur: list = []
+    rows_cur = 0
+    lrow_cur = 0
+
+    def flush():
+        nonlocal cur, rows_cur, lrow_cur
+        if not cur:
+            return
+        rows = np.concatenate([batches[i].rows for i in cur])
+        lpad = np.concatenate([np.full(batches[i].rows.size, batches[i].Lpad, np.int32) for i in cur])
+        members, r0 = [], 0
+        for i in cur:
+            members.append((i, r0, r0 + batches[i].rows.size, batches[i]))
+            r0 += batches[i].rows.size
+        out.append(Launch(rows, lpad, int(lpad.max()), lrow_cur, members))
+        cur, rows_cur, lrow_cur = [], 0, 0
+
+    lrow_first = 0
+    for i in order:
+        b = batches[i]
+        lrow = max(lrow_cur, b.Lrow)
+        # a launch closes when the budget is reached, or -- once it holds a full 128-row tile -- when the next batch is
+        # more than an eighth longer than its first one (every row is right-filled to the longest member's stride)
+        if cur and ((rows_cur + b.rows.size) * lrow > token_budget or
+                    (rows_cur >= ROW_TILE and 8 * lrow > 9 * lrow_first)):
+            flush()
+            lrow = b.Lrow
+        if not cur:
+            lrow_first = b.Lrow
+        cur.append(i)
+        rows_cur += b.rows.size
+        lrow_cur = lrow
+    flush()
+    return out
+
+
 def shard_batches(batches: Sequence[Batch], rank: int, world: int) -> List[Batch]:
     """Deal batches to ranks greedily by padded token count: no collective on the path."""
     if world <= 1:

@@ -117,6 +117,15 @@ int64_t dcb200_ctx_get_option(dcb200_ctx* ctx, const char* name);
  * columns < Lpad. */
 int dcb200_encode_batch(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
                         const int32_t* len, int32_t R, int32_t Lpad, int32_t Lrow, uint8_t* tok, float* qual);
+/* Several of the reference's batches in ONE launch: row r is collated as in ITS batch, i.e. left-padded to
+ * lpad_rows[r] (device array; len[r] + 1 <= lpad_rows[r] <= Lpad), and right-filled to Lrow like every row.  The reference
+ * pads a FASTQ-order batch of 12-16 reads to that batch's maximum (deepchopper/data/only_fq.py:198-202,
+ * deepchopper/models/llm/tokenizer.py:34-93) and the pads are semantic, so a row must keep its own batch's pad count; the
+ * model is causal and rows are independent, so rows of many such batches can share a launch (full 128-row tiles instead
+ * of 16 rows) without changing what any of them sees in columns < lpad_rows[r]. */
+int dcb200_encode_batch_rows(dcb200_ctx* ctx, const uint8_t* bytes, const int64_t* seq_off, const int64_t* qual_off,
+                             const int32_t* len, const int32_t* lpad_rows, int32_t R, int32_t Lpad, int32_t Lrow,
+                             uint8_t* tok, float* qual);
 
 /* ---- weights ------------------------------------------------------------------------------------
  * State dict as parallel arrays of names / host fp32 pointers / element counts.  Names are the

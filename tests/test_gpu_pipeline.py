@@ -179,6 +179,58 @@ def test_fused_predict_chop_equals_two_step(tmp_path):
     assert a == b and len(a) > 0
 
 
+def test_grouped_reference_batches_equal_one_launch_per_batch(tmp_path):
+    """The reference's FASTQ-order batches packed into launches (predict.group_batches + dcb200_encode_batch_rows): a row's
+    tokens / quality equal those of its own batch's collation, and -- with one long-convolution kernel for both runs --
+    `predict --chop -b 16` writes the same bytes whether a launch holds one batch or forty (causal model, independent
+    rows: the right filler and the neighbours cannot reach a row's first Lpad columns)."""
+    from deepchopper_b200 import _native, cli, ops  # noqa: F401
+    from deepchopper_b200.encode import encode_batch_device
+    from deepchopper_b200.predict import Batch, group_batches
+    rng = np.random.default_rng(29)
+    lens = np.concatenate([synth.read_lengths(rng, 500, hi=5000), rng.integers(20, 150, 20)])
+    rng.shuffle(lens)
+    recs = synth.fastq_reads(rng, lens.size, lengths=lens)
+    # (a) encode_rows == encode per batch
+    blob = np.frombuffer(("".join(r[1] for r in recs) + "".join(r[2] for r in recs)).encode(), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    dev = torch.device("cuda", 0)
+    d_blob = torch.from_numpy(blob.copy()).to(dev)
+    batches = []
+    for i in range(0, lens.size, 16):
+        rows = np.arange(i, min(i + 16, lens.size))
+        lp = int(lens[rows].max()) + 1
+        batches.append(Batch(rows, lp, (lp + 127) // 128 * 128))
+    launches = group_batches(batches, 256 * 1024)
+    assert len(launches) < len(batches) / 4
+    tot = int(lens.sum())
+    for g in launches[:3]:
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(dev)  # noqa: E731
+        tok, qual = torch.ops.dcb200.encode_rows(d_blob, t(off[g.rows], np.int64), t(off[g.rows] + tot, np.int64),
+                                                 t(lens[g.rows], np.int32), t(g.lpad, np.int32), int(g.Lpad), int(g.Lrow))
+        for pos, r0, r1, b in g.members:
+            tk, ql = encode_batch_device(d_blob, t(off[b.rows], np.int64), t(off[b.rows] + tot, np.int64),
+                                         t(lens[b.rows], np.int32), b.Lpad, None, b.Lrow)
+            assert torch.equal(tok[r0:r1, :b.Lrow], tk) and torch.equal(qual[r0:r1, :b.Lrow], ql)
+            assert (tok[r0:r1, b.Lrow:] == 4).all() and (qual[r0:r1, b.Lrow:] == 0).all()
+    # (b) the fused route, one batch per launch vs grouped launches, Toeplitz kernel for both
+    fq = _write_fastq(tmp_path, recs)
+    ctx = _native.torch_context(dev)
+    old = ctx.get_option("fft_min_len")
+    ctx.set_option("fft_min_len", 1 << 30)
+    try:
+        common = ["predict", str(fq), "--chop", "--random-init", "-b", "16", "-t", "4"]
+        cli.main(common + ["--chop-output", str(tmp_path / "single"), "--token-budget", "1"])
+        cli.main(common + ["--chop-output", str(tmp_path / "grouped"), "--token-budget", "262144"])
+    finally:
+        ctx.set_option("fft_min_len", old)
+    a = [f for f in os.listdir(tmp_path) if f.startswith("single.")]
+    b = [f for f in os.listdir(tmp_path) if f.startswith("grouped.")]
+    assert len(a) == 1 and len(b) == 1 and a[0][len("single"):] == b[0][len("grouped"):]
+    ta, tb = gzip.open(tmp_path / a[0], "rb").read(), gzip.open(tmp_path / b[0], "rb").read()
+    assert ta == tb and len(ta) > 0
+
+
 def test_truncated_read_passes_through(tmp_path):
     """A read of >= 32768 bases is cut to the model's window and flagged (tokenizer.py:154-163); `chop` then refuses to
     cut it (prediction length != FASTQ quality length, src/bin/predict.rs:160-164) and emits the record verbatim.  The

@@ -37,6 +37,33 @@ def test_plan_batches_covers_every_read_once():
     assert all(np.array_equal(b.rows, np.arange(i * 12, min(lens.size, (i + 1) * 12))) for i, b in enumerate(fb))
 
 
+def test_group_batches_keeps_each_batch_collation():
+    """predict.group_batches: FASTQ-order batches packed into launches; every row keeps its own batch's collated length,
+    every batch lands in exactly one launch, rows stay in batch order, the token budget holds (single-batch launches aside)."""
+    from deepchopper_b200.predict import Batch, group_batches
+    rng = np.random.default_rng(4)
+    lens = np.clip(np.round(rng.lognormal(np.log(1000), 0.6, 3000)), 200, 32767).astype(np.int64)
+    batches = []
+    for i in range(0, lens.size, 12):
+        rows = np.arange(i, min(i + 12, lens.size))
+        lp = int(lens[rows].max()) + 1
+        batches.append(Batch(rows, lp, (lp + 127) // 128 * 128))
+    for budget in (1 << 20, 1 << 16, 1):
+        launches = group_batches(batches, budget)
+        seen = sorted(pos for g in launches for pos, _, _, _ in g.members)
+        assert seen == list(range(len(batches)))
+        for g in launches:
+            assert g.Lrow % 128 == 0 and g.Lpad == int(g.lpad.max()) and g.Lpad <= g.Lrow
+            assert g.rows.size * g.Lrow <= budget or len(g.members) == 1
+            for pos, r0, r1, b in g.members:
+                assert b is batches[pos] and np.array_equal(g.rows[r0:r1], b.rows)
+                assert (g.lpad[r0:r1] == b.Lpad).all() and b.Lrow <= g.Lrow
+        if budget == 1:
+            assert len(launches) == len(batches)
+    padded = sum(g.rows.size * g.Lrow for g in group_batches(batches, 1 << 20))
+    assert padded <= 1.2 * sum(b.rows.size * b.Lrow for b in batches)      # similar lengths share a launch
+
+
 def test_shard_batches_partition():
     rng = np.random.default_rng(1)
     bs = plan_batches(synth.read_lengths(rng, 20000))
