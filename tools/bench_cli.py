@@ -2,7 +2,10 @@
   A  `predict --chop`                      one pass, no prediction files (deepchopper_b200/fused.py)
   B  `predict --compact` then `chop`       bit-packed label sidecars
   C  `predict` then `chop`                 the reference's .pt dicts (28 bytes per token)
-and whether the three outputs are byte-identical.    python tools/bench_cli.py [reads] [routes, e.g. AB]"""
+  D  `predict --chop -b 16`                one pass in the REFERENCE's batching (FASTQ order, batch 16, batches packed into
+                                           launches with every row padded as in its own batch); not compared with A-C:
+                                           left pads are semantic, so its logits are those of other batches
+and whether the outputs of A-C are byte-identical.    python tools/bench_cli.py [reads] [routes, e.g. AB]"""
 import glob
 import gzip
 import hashlib
@@ -64,5 +67,9 @@ if "C" in routes:
     t2 = run(py + ["chop", os.path.join(d, "predC", "0"), fq, "-t", "16", "-o", os.path.join(d, "C"), "-v"])
     digest["C"] = out_digest("C")
     print(f"C predict {t1:.2f} s ({sz / 1e6:.0f} MB of .pt) + chop {t2:.2f} s = {bases / (t1 + t2) / 1e6:.2f} M bases/s")
+if "D" in routes:
+    t = run(py + ["predict", fq, "--chop", "--chop-output", os.path.join(d, "D"), "-t", "16", "--random-init", "-b", "16",
+                  "--token-budget", str(1024 * 1024), "-v"])
+    print(f"D predict --chop -b 16 (reference batching): {t:.2f} s wall = {bases / t / 1e6:.2f} M bases/s (start-up included)")
 print("outputs:", digest, "identical:", len(set(digest.values())) == 1)
 print(f"peak RSS of the children: {resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1024:.0f} MB")
