@@ -498,6 +498,23 @@ def extra_reference_batching(model, args, dev, n_reads: int = 1536):
             _, labels = model.forward_tokens(tok, qual, False, True)
             smooth_chop_device(labels.view(-1), st, ln)
 
+    # the same launches through the C ABI on pinned host buffers (dcb200_predict_batch_host_rows)
+    hg = HostPipeline(model)
+    g_items = []
+    for g in groups:
+        ln = lens[g.rows].astype(np.int32)
+        so = (np.cumsum(ln) - ln).astype(np.int64)
+        buf = np.concatenate([blob[off[r]:off[r] + lens[r]] for r in g.rows] + [blob[tot + off[r]:tot + off[r] + lens[r]] for r in g.rows])
+        g_items.append((g, buf, so, so + int(ln.sum()), ln))
+    hg.pack_items(g_items)
+    hg.run_all()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hg.run_all()
+    torch.cuda.synchronize(dev)
+    e2e_g = time.perf_counter() - t0
+    del hg
     run_groups()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -517,6 +534,7 @@ def extra_reference_batching(model, args, dev, n_reads: int = 1536):
             "batches_per_step": len(batches), "steps": steps, "ms_per_step": ms_g / steps,
             "padded_tokens_per_sec": tokens_g * steps / (ms_g / 1e3), "padding_overhead": tokens_g / max(1, bases),
             "route": "batches packed into launches, every row left-padded as in its own batch (group_batches)",
+            "e2e": {"value": bases * steps / e2e_g, "unit": UNIT, "api": "dcb200_predict_batch_host_rows, one call per launch"},
             "one_batch_per_launch": {"value": bases * steps / (ms / 1e3), "unit": UNIT, "ms_per_batch": ms / steps / len(batches),
                                      "gpu_launches": int(launches), "padding_overhead": tokens / max(1, bases),
                                      "e2e": {"value": bases * steps / e2e_s, "unit": UNIT,

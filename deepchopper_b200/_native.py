@@ -12,7 +12,7 @@ EXPORTS = [
     "dcb200_last_error", "dcb200_version", "dcb200_chop_params_default", "dcb200_ctx_create", "dcb200_ctx_destroy",
     "dcb200_ctx_sync", "dcb200_ctx_stream", "dcb200_ctx_launch_count", "dcb200_encode_batch", "dcb200_encode_batch_rows", "dcb200_weights_create",
     "dcb200_weights_destroy", "dcb200_forward", "dcb200_smooth_chop", "dcb200_smooth_chop_logits",
-    "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host",
+    "dcb200_majority_voting", "dcb200_smooth_chop_host", "dcb200_majority_voting_host", "dcb200_predict_batch_host", "dcb200_predict_batch_host_rows",
     "dcb200_forward_debug", "dcb200_ctx_read_workspace", "dcb200_ctx_profile", "dcb200_ctx_profile_read",
     "dcb200_kernel_kind_name", "dcb200_chop_write_bgzf",
     "dcb200_read_file_inflate", "dcb200_free", "dcb200_ctx_set_option", "dcb200_ctx_get_option",
@@ -103,6 +103,7 @@ def lib():
     l.dcb200_smooth_chop_host.argtypes = [vp, vp, i64, vp, vp, vp, i64, pp, vp, vp, vp, vp, vp]
     l.dcb200_majority_voting_host.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]
     l.dcb200_predict_batch_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, pp, vp, vp, vp, vp, vp, vp, vp]
+    l.dcb200_predict_batch_host_rows.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, i32, pp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("dcb200_last_error", "dcb200_chop_params_default", "dcb200_ctx_stream", "dcb200_ctx_launch_count",
                         "dcb200_kernel_kind_name", "dcb200_ctx_get_option", "dcb200_free"):

@@ -29,9 +29,10 @@ int weights_destroy(dcb200_weights* w);
 int forward_device(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* tok, const float* qual, int32_t B, int32_t L,
                    float* logits, uint8_t* labels, int stop_stage);
 
-__global__ void row_starts_kernel(const int32_t* __restrict__ len, int R, int Lrow, int Lpad, int64_t* __restrict__ starts) {
+__global__ void row_starts_kernel(const int32_t* __restrict__ len, const int32_t* __restrict__ lpad_rows, int R, int Lrow,
+                                  int Lpad, int64_t* __restrict__ starts) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) starts[r] = (int64_t)r * Lrow + (Lpad - 1 - len[r]);
+  if (r < R) starts[r] = (int64_t)r * Lrow + ((lpad_rows ? lpad_rows[r] : Lpad) - 1 - len[r]);
 }
 
 static int check_params(const dcb200_chop_params* p) {
@@ -369,11 +370,13 @@ int dcb200_majority_voting_host(dcb200_ctx* ctx, const int8_t* labels, int64_t l
   return DCB200_OK;
 }
 
-int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
-                              const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
-                              const int32_t* qual_lens, int32_t R, int32_t Lpad, const dcb200_chop_params* p,
-                              float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
-                              int32_t* n_keep, int32_t* keep_iv, uint8_t* action) {
+}  // extern "C"
+
+static int predict_batch_host_impl(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
+                                   const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
+                                   const int32_t* lpad_rows, const int32_t* qual_lens, int32_t R, int32_t Lpad,
+                                   const dcb200_chop_params* p, float* logits_out, uint8_t* labels_out, int32_t* n_adapter,
+                                   int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv, uint8_t* action) {
   DCB_ARG(ctx && w && bytes && seq_off && qual_off && len && n_adapter && adapter_iv && n_keep && keep_iv && action);
   DCB_ARG(R > 0 && n_bytes > 0 && Lpad > 0 && Lpad <= 32768);
   DCB_CHECK(check_params(p));
@@ -381,23 +384,26 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   const int ap = p->approved_interval_number;
   const int Lrow = (Lpad + 127) / 128 * 128;  // row stride; columns >= Lpad are inert right filler (causal model)
   const size_t T = (size_t)R * Lrow;
-  void *d_bytes, *d_so, *d_qo, *d_len, *d_ql = nullptr, *d_tok, *d_q, *d_lab, *d_logits = nullptr, *d_st;
+  void *d_bytes, *d_so, *d_qo, *d_len, *d_ql = nullptr, *d_tok, *d_q, *d_lab, *d_logits = nullptr, *d_st, *d_lp = nullptr;
   void *d_na, *d_ad, *d_nk, *d_kp, *d_act;
   DCB_CHECK(stage_in(ctx, "p_bytes", bytes, (size_t)n_bytes, &d_bytes));
   DCB_CHECK(stage_in(ctx, "p_seq_off", seq_off, (size_t)R * 8, &d_so));
   DCB_CHECK(stage_in(ctx, "p_qual_off", qual_off, (size_t)R * 8, &d_qo));
   DCB_CHECK(stage_in(ctx, "p_len", len, (size_t)R * 4, &d_len));
   if (qual_lens) DCB_CHECK(stage_in(ctx, "p_qlens", qual_lens, (size_t)R * 4, &d_ql));
+  if (lpad_rows) DCB_CHECK(stage_in(ctx, "p_lpad_rows", lpad_rows, (size_t)R * 4, &d_lp));
   // a bad offset from across the plain-pointer ABI must not become an out-of-bounds device read
   DCB_ARG((int64_t)R * Lrow <= INT_MAX / 2);
   for (int r = 0; r < R; ++r) {
-    DCB_ARG(len[r] >= 0 && len[r] + 1 <= Lpad);
+    DCB_ARG(len[r] >= 0 && len[r] + 1 <= (lpad_rows ? lpad_rows[r] : Lpad));
+    DCB_ARG(!lpad_rows || lpad_rows[r] <= Lpad);
     DCB_ARG(seq_off[r] >= 0 && seq_off[r] + len[r] <= n_bytes && qual_off[r] >= 0 && qual_off[r] + len[r] <= n_bytes);
   }
   // label-row starts: read r occupies columns [Lpad-len-1, Lpad-1) of row r (left pad, SEP last); computed on the device
   // from the lengths that are uploaded anyway (no host staging vector, no extra synchronisation)
   DCB_CHECK(stage_out(ctx, "p_starts", (size_t)R * 8, &d_st));
-  row_starts_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>((const int32_t*)d_len, R, Lrow, Lpad, (int64_t*)d_st);
+  row_starts_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>((const int32_t*)d_len, (const int32_t*)d_lp, R, Lrow, Lpad,
+                                                              (int64_t*)d_st);
   DCB_LAUNCH_CHECK(ctx);
   DCB_CHECK(stage_out(ctx, "p_tok", T, &d_tok));
   DCB_CHECK(stage_out(ctx, "p_qual", T * 4, &d_q));
@@ -410,7 +416,8 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   DCB_CHECK(stage_out(ctx, "h_act", (size_t)R, &d_act));
   DCB_CUDA(cudaMemsetAsync(d_ad, 0, (size_t)R * ap * 8, ctx->stream));
   DCB_CUDA(cudaMemsetAsync(d_kp, 0, (size_t)R * (ap + 1) * 8, ctx->stream));
-  DCB_CHECK(encode_device(ctx, (const uint8_t*)d_bytes, (const int64_t*)d_so, (const int64_t*)d_qo, (const int32_t*)d_len, nullptr, R,
+  DCB_CHECK(encode_device(ctx, (const uint8_t*)d_bytes, (const int64_t*)d_so, (const int64_t*)d_qo, (const int32_t*)d_len,
+                          (const int32_t*)d_lp, R,
                           Lpad, Lrow, (uint8_t*)d_tok, (float*)d_q));
   DCB_CHECK(forward_device(ctx, w, (const uint8_t*)d_tok, (const float*)d_q, R, Lrow, (float*)d_logits, (uint8_t*)d_lab, 1 << 30));
   DCB_CHECK(smooth_chop_device(ctx, (const int8_t*)d_lab, nullptr, (int64_t)T, (const int64_t*)d_st, (const int32_t*)d_len,
@@ -429,6 +436,27 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
   DCB_CUDA(cudaMemcpyAsync(action, d_act, (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
   DCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return DCB200_OK;
+}
+
+extern "C" {
+
+int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
+                              const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
+                              const int32_t* qual_lens, int32_t R, int32_t Lpad, const dcb200_chop_params* p,
+                              float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
+                              int32_t* n_keep, int32_t* keep_iv, uint8_t* action) {
+  return predict_batch_host_impl(ctx, w, bytes, n_bytes, seq_off, qual_off, len, nullptr, qual_lens, R, Lpad, p, logits_out,
+                                 labels_out, n_adapter, adapter_iv, n_keep, keep_iv, action);
+}
+
+int dcb200_predict_batch_host_rows(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
+                                   const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
+                                   const int32_t* lpad_rows, const int32_t* qual_lens, int32_t R, int32_t Lpad,
+                                   const dcb200_chop_params* p, float* logits_out, uint8_t* labels_out, int32_t* n_adapter,
+                                   int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv, uint8_t* action) {
+  DCB_ARG(lpad_rows != nullptr);
+  return predict_batch_host_impl(ctx, w, bytes, n_bytes, seq_off, qual_off, len, lpad_rows, qual_lens, R, Lpad, p, logits_out,
+                                 labels_out, n_adapter, adapter_iv, n_keep, keep_iv, action);
 }
 
 }  // extern "C"

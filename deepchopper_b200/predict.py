@@ -261,6 +261,13 @@ class HostPipeline:
     def run_batch(self, item, labels_out: Optional[np.ndarray] = None, logits_out: Optional[np.ndarray] = None):
         b, buf, so, qo, ln, o = item
         p = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        if isinstance(b, Launch):   # several FASTQ-order batches, every row padded as in its own batch
+            check(lib().dcb200_predict_batch_host_rows(
+                self.ctx.handle, self.model._weights.handle, C.c_void_p(buf.data_ptr()), buf.numel(), p(so), p(qo), p(ln),
+                p(b.lpad), None, int(b.rows.size), int(b.Lpad), C.byref(self.params),
+                p(logits_out) if logits_out is not None else None, p(labels_out) if labels_out is not None else None,
+                p(o["n_adapter"]), p(o["adapter_iv"]), p(o["n_keep"]), p(o["keep_iv"]), p(o["action"])))
+            return o
         check(lib().dcb200_predict_batch_host(
             self.ctx.handle, self.model._weights.handle, C.c_void_p(buf.data_ptr()), buf.numel(), p(so), p(qo), p(ln),
             None, int(b.rows.size), int(b.Lpad), C.byref(self.params),

@@ -183,6 +183,15 @@ int dcb200_predict_batch_host(dcb200_ctx* ctx, const dcb200_weights* w, const ui
                               const int32_t* qual_lens, int32_t R, int32_t Lpad, const dcb200_chop_params* p,
                               float* logits_out, uint8_t* labels_out, int32_t* n_adapter, int32_t* adapter_iv,
                               int32_t* n_keep, int32_t* keep_iv, uint8_t* action);
+/* The same with several of the reference's FASTQ-order batches in one call (see dcb200_encode_batch_rows): row r is
+ * left-padded to lpad_rows[r] (host array, len[r] + 1 <= lpad_rows[r] <= Lpad), the collated length of ITS batch.
+ * logits_out / labels_out keep the row width Lpad; row r's read sits in columns [lpad_rows[r] - 1 - len[r], lpad_rows[r] - 1),
+ * its SEP in column lpad_rows[r] - 1, columns beyond are filler. */
+int dcb200_predict_batch_host_rows(dcb200_ctx* ctx, const dcb200_weights* w, const uint8_t* bytes, int64_t n_bytes,
+                                   const int64_t* seq_off, const int64_t* qual_off, const int32_t* len,
+                                   const int32_t* lpad_rows, const int32_t* qual_lens, int32_t R, int32_t Lpad,
+                                   const dcb200_chop_params* p, float* logits_out, uint8_t* labels_out, int32_t* n_adapter,
+                                   int32_t* adapter_iv, int32_t* n_keep, int32_t* keep_iv, uint8_t* action);
 
 /* ---- chop output: record assembly + BGZF on host threads ---------------------------------------------
  * Replaces the write loop of `deepchopper-chop` (src/bin/predict.rs:266-364), the record naming / slicing of

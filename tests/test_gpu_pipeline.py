@@ -213,6 +213,34 @@ def test_grouped_reference_batches_equal_one_launch_per_batch(tmp_path):
                                          t(lens[b.rows], np.int32), b.Lpad, None, b.Lrow)
             assert torch.equal(tok[r0:r1, :b.Lrow], tk) and torch.equal(qual[r0:r1, :b.Lrow], ql)
             assert (tok[r0:r1, b.Lrow:] == 4).all() and (qual[r0:r1, b.Lrow:] == 0).all()
+    # (a') the host-buffer C entry for such a launch (dcb200_predict_batch_host_rows) == the three device ops
+    from deepchopper_b200.init_weights import random_state_dict
+    from deepchopper_b200.model import DeepChopper
+    from deepchopper_b200.predict import HostPipeline
+    from deepchopper_b200.smooth import smooth_chop_device
+    model = DeepChopper.from_state_dict(random_state_dict(0), device=0)
+    hp = HostPipeline(model)
+    items = []
+    for g in launches[:2]:
+        ln = lens[g.rows].astype(np.int32)
+        so = (np.cumsum(ln) - ln).astype(np.int64)
+        buf = np.concatenate([blob[off[r]:off[r] + lens[r]] for r in g.rows] + [blob[tot + off[r]:tot + off[r] + lens[r]] for r in g.rows])
+        items.append((g, buf, so, so + int(ln.sum()), ln))
+    hp.pack_items(items, pin=False)
+    for g, hi in zip(launches[:2], hp.items):
+        labels_h = np.zeros((g.rows.size, g.Lpad), np.uint8)
+        o = hp.run_batch(hi, labels_h)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(dev)  # noqa: E731
+        ln_d, lp_d = t(lens[g.rows], np.int32), t(g.lpad, np.int32)
+        tok, qual = torch.ops.dcb200.encode_rows(d_blob, t(off[g.rows], np.int64), t(off[g.rows] + tot, np.int64), ln_d, lp_d,
+                                                 int(g.Lpad), int(g.Lrow))
+        _, labels_d = model.forward_tokens(tok, qual, False, True)
+        st = torch.arange(g.rows.size, dtype=torch.int64, device=dev) * g.Lrow + (lp_d.to(torch.int64) - 1) - ln_d.to(torch.int64)
+        n_ad, ad, n_keep, keep, act = smooth_chop_device(labels_d.view(-1), st, ln_d)
+        torch.cuda.synchronize()
+        assert np.array_equal(labels_d.cpu().numpy()[:, :g.Lpad], labels_h)
+        assert np.array_equal(o["n_adapter"], n_ad.cpu().numpy()) and np.array_equal(o["action"], act.cpu().numpy())
+        assert np.array_equal(o["adapter_iv"], ad.cpu().numpy()) and np.array_equal(o["keep_iv"], keep.cpu().numpy())
     # (b) the fused route, one batch per launch vs grouped launches, Toeplitz kernel for both
     fq = _write_fastq(tmp_path, recs)
     ctx = _native.torch_context(dev)
