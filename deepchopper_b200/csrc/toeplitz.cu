@@ -37,7 +37,8 @@ constexpr uint32_t kTzWin = 40 * 128;           // bytes of one E window
 constexpr uint32_t kTzStage = 128 * 128 + 6144; // stage pitch (keeps the A tiles 1024-byte aligned)
 // 16 KB each.  A slot is released one box late (when the NEXT store has been issued and this one's read is done), so
 // with 3 slots only one gate box could be in flight: 4 slots are worth 6-7 % at L = 1280 (HBM-bound regime); a fifth
-// slot, or more A stages, change nothing.  Tried and dropped: L2 prefetch of the next item's first 512 tokens (+11 %).
+// slot, or more A stages, change nothing.  Tried and dropped: L2 prefetch of the next item's first 512 tokens (+11 %);
+// one store per TMEM lane quadrant behind 64-thread barriers instead of one per box behind a 256-thread one (no change).
 constexpr int kTzGSlots = 4;
 constexpr int kTzZeroChunks = 32;
 constexpr uint32_t kTzBox = 128 * 128;  // bytes of one TMA box
