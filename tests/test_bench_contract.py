@@ -57,3 +57,16 @@ def test_bench_global_job_is_rank_independent():
     buf, so, qo, ln = items_a[0][1:]
     assert buf.size == 2 * int(ln.sum()) and set(np.unique(buf[: int(ln.sum())])) <= set(b"ACGTN")
     assert buf[int(ln.sum()):].min() >= 34 and buf[int(ln.sum()):].max() <= 83 and qo[0] == int(ln.sum())
+
+
+def test_takes_fft_mirror_of_the_cost_model():
+    """bench.takes_fft mirrors model.cu:use_fft_conv (the GPU test checks that the kernels actually launched agree with
+    it): full 128-row tiles take the FFT from ~6.7 k tokens, not while a second block is mostly empty, and always above
+    ~9.9 k; a 16-row batch from ~3.4 k tokens; an explicit fft_min_len is a plain threshold; nothing beyond 32768."""
+    import bench
+    d = 6144
+    assert not bench.takes_fft(6656, d) and bench.takes_fft(6784, d) and bench.takes_fft(8192, d)
+    assert not bench.takes_fft(8320, d) and not bench.takes_fft(9856, d) and bench.takes_fft(9984, d) and bench.takes_fft(32768, d)
+    assert not bench.takes_fft(3200, d, 16) and bench.takes_fft(3456, d, 16)
+    assert not bench.takes_fft(6144, d, 64) and bench.takes_fft(6784, d, 200)
+    assert bench.takes_fft(128, 0) and not bench.takes_fft(32768, 1 << 30) and not bench.takes_fft(32896, 0)
