@@ -1,6 +1,6 @@
-// Segmented warp-level smoothing / interval / chop-coordinate kernel.
+// Smoothing / interval / chop-coordinate kernels.
 //
-// Replaces, per read, the reference's CPU chain
+// Replace, per read, the reference's CPU chain
 //   majority_voting        src/smooth/utils.rs:48-97
 //   get_label_region       src/utils.rs:671-695         (start==0 sentinel quirk kept: position 0 is masked)
 //   smooth_and_select_intervals  src/smooth/predict.rs:186-209
@@ -8,11 +8,16 @@
 //                          src/output/split.rs:60-136,171-201,260-292
 //   process_chunk gating   src/bin/predict.rs:141-164
 //
-// One warp owns one read.  Labels are packed to a bit stream (32 bases per lane-word, 1024 bases per
-// warp step); the majority vote over the default 21-wide window is a bit-sliced carry-save adder tree
-// on those words (all 32 positions of a lane at once), run boundaries are found with shifts/ballots,
-// and intervals are emitted in order with a warp prefix sum.  HBM traffic is the 1 byte per base of
-// the labels (8 B/base when reading fp32 logits) plus <= a few dozen bytes of coordinates per read.
+// Labels are packed to a bit stream (32 bases per word); the majority vote over the default 21-wide window is a
+// bit-sliced carry-save adder tree on those words (all 32 positions of a word at once).  Two kernels, bit-exact with
+// each other and with the oracle:
+//   smooth_chop_kernel  one WARP per read, a word per lane, 1024 bases per step, neighbours by shuffle, run boundaries
+//                       with shifts / ballots, ordered emission by warp prefix sum.  Takes int8 labels or fp32 logits,
+//                       any read length, optional smoothed-label output; used for small launches (a batch inside
+//                       predict), the logits form, majority_voting, and reads beyond 32768 bases.
+//   smooth_tile_kernel  one THREAD per word, a CTA per 64 reads (int8 labels, big launches): see its header below.
+// HBM traffic is the 1 byte per base of the labels (8 B/base when reading fp32 logits) plus <= a few dozen bytes of
+// coordinates per read.
 #include "common.cuh"
 
 namespace dcb {
