@@ -5,7 +5,9 @@
 // never exists.  HBM traffic per token: read u (512 B), write vv + gate (1 KB).
 //
 // One persistent CTA per SM (a CTA-pair variant with M = 256 MMAs measured 5 % slower: the kernel is bound by waits
-// around the MMA series, not by the MMA rate).  A work unit is (128-token tile, 128-channel group): three tcgen05 MMA series
+// around the MMA series, not by the MMA rate: with a full weight ring a 64-wide K stage issues every ~275 cycles, the
+// nominal rate; the waits are the ring -- 112 KB in flight per ~3 k cycles of loaded L2 latency, 37 B/clk per SM, ~5.5
+// KB/clk over the chip, i.e. the L2 output limit: 3 KB of weights per token -- and the first box of the next u tile).  A work unit is (128-token tile, 128-channel group): three tcgen05 MMA series
 //   x1 = W_in[256+c..] . u^T ,  v = W_in[512+c..] . u^T ,  x0 = W_in[c..] . u^T        (M = 128 channels, K = 256)
 // with N = 144 tokens: the tile plus the 16 tokens before it, so the causal 3-tap convolution (which needs z[t-1],
 // z[t-2]) has its halo in the same accumulator and tiles stay independent.  The accumulator rows are channels, so an
